@@ -1,0 +1,299 @@
+// Selector-specific kernels: the HBM-bound correlation + rotated-similarity score (S2), the
+// closed-form first-InstanceNorm statistics, and the small latency-bound tail ops (S4).
+#include "common.cuh"
+
+namespace g6d {
+
+// ------------------------------------------------------------------------------------------
+// S2: score[s] = sum_p t_p^2 / max_p t_p with t_p = sum_c q[p,c] * ref[s,p,c]
+// (selector.py:183-186,192-194).  ref [S,P,C] is read exactly once, as 128-bit streaming loads:
+// one warp owns a position p of a slice (C = 512 -> 4 float4 per lane, 2 KB contiguous), the
+// query row q[p,:] comes from L1/L2 (0.69 MB total, reused by every slice), the 512-term dot is
+// finished with warp shuffles, and the per-slice sum/max with one shared-memory step.
+// Grid: persistent-style, blockIdx.x strides over slices so the grid is a multiple of the SM
+// count regardless of S.
+template <int C>
+__global__ void __launch_bounds__(256) sel_corr_score_kernel(const float* __restrict__ ref,
+                                                             const float* __restrict__ q, int S, int P,
+                                                             float* __restrict__ score) {
+    constexpr int V = C / 128;  // float4 per lane
+    extern __shared__ float t_sh[];  // [P] per-location inner products of the current slice
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int nwarp = blockDim.x >> 5;
+    __shared__ float s_red[8];
+    for (int s = blockIdx.x; s < S; s += gridDim.x) {
+        const float4* rs = reinterpret_cast<const float4*>(ref + (long long)s * P * C);
+        float mx = -INFINITY;
+        for (int p = warp; p < P; p += nwarp) {
+            const float4* rp = rs + (long long)p * (C / 4);
+            const float4* qp = reinterpret_cast<const float4*>(q + (long long)p * C);
+            float4 rv[V];
+#pragma unroll
+            for (int i = 0; i < V; ++i) rv[i] = ldg_stream(rp + lane + 32 * i);
+            float t = 0.f;
+#pragma unroll
+            for (int i = 0; i < V; ++i) {
+                const float4 qv = __ldg(qp + lane + 32 * i);
+                t = fmaf(rv[i].x, qv.x, fmaf(rv[i].y, qv.y, fmaf(rv[i].z, qv.z, fmaf(rv[i].w, qv.w, t))));
+            }
+            t = warp_sum(t);
+            if (lane == 0) t_sh[p] = t;
+            mx = fmaxf(mx, t);
+        }
+        if (lane == 0) s_red[warp] = mx;
+        __syncthreads();
+        float m = s_red[0];
+        for (int w = 1; w < nwarp; ++w) m = fmaxf(m, s_red[w]);
+        __syncthreads();
+        // score = sum_p t * (t / max), with the reference's operation order (selector.py:193-194)
+        // and IEEE behaviour when max <= 0 (no epsilon in the reference).
+        float acc = 0.f;
+        for (int p = threadIdx.x; p < P; p += blockDim.x) { const float t = t_sh[p]; acc += t * (t / m); }
+        acc = warp_sum(acc);
+        if (lane == 0) s_red[warp] = acc;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            float a = 0.f;
+            for (int w = 0; w < nwarp; ++w) a += s_red[w];
+            score[s] = a;
+        }
+        __syncthreads();
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// sum_s ref and sum_s ref^2 over the slice axis, doubles [P*C].  Load-time (once per object).
+__global__ void sel_ref_sums_kernel(const float* __restrict__ ref, int S, long long PC, int s_chunk,
+                                    double* __restrict__ sum1, double* __restrict__ sum2) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= PC) return;
+    const int s0 = blockIdx.y * s_chunk, s1 = min(S, s0 + s_chunk);
+    double a = 0.0, b = 0.0;
+    for (int s = s0; s < s1; ++s) {
+        const double v = (double)ref[(long long)s * PC + i];
+        a += v; b += v * v;
+    }
+    atomicAdd(sum1 + i, a);
+    atomicAdd(sum2 + i, b);
+}
+
+// Per channel c: mean_c = sum_p q[p,c]*A[p,c] / N, E2_c = sum_p q[p,c]^2*B[p,c] / N, N = S*P;
+// then scale[p,c] = q[p,c]*rstd_c and shift[c] = -mean_c*rstd_c.  One block per 32 channels.
+__global__ void sel_corr_prologue_kernel(const float* __restrict__ q, const double* __restrict__ sum1,
+                                         const double* __restrict__ sum2, int S, int P, int C, float eps,
+                                         float* __restrict__ scale, float* __restrict__ shift) {
+    const int c = blockIdx.x * 32 + (threadIdx.x & 31);
+    const int row = threadIdx.x >> 5, nrow = blockDim.x >> 5;
+    __shared__ double sm[8][32], sv[8][32];
+    __shared__ float s_rstd[32];
+    double m = 0.0, e2 = 0.0;
+    if (c < C) {
+        for (int p = row; p < P; p += nrow) {
+            const double qv = (double)q[(long long)p * C + c];
+            m += qv * sum1[(long long)p * C + c];
+            e2 += qv * qv * sum2[(long long)p * C + c];
+        }
+    }
+    sm[row][threadIdx.x & 31] = m; sv[row][threadIdx.x & 31] = e2;
+    __syncthreads();
+    if (row == 0 && c < C) {
+        for (int r = 1; r < nrow; ++r) { m += sm[r][threadIdx.x]; e2 += sv[r][threadIdx.x]; }
+        const double n = (double)S * (double)P;
+        const double mean = m / n;
+        double var = e2 / n - mean * mean;
+        var = var < 0.0 ? 0.0 : var;
+        const double rstd = 1.0 / sqrt(var + (double)eps);
+        s_rstd[threadIdx.x] = (float)rstd;
+        shift[c] = (float)(-mean * rstd);
+    }
+    __syncthreads();
+    if (c < C) {
+        const float r = s_rstd[threadIdx.x & 31];
+        for (int p = row; p < P; p += nrow) scale[(long long)p * C + c] = q[(long long)p * C + c] * r;
+    }
+}
+
+// vp_norm: InstanceNorm2d over n values per level; scatter to feats[i, coff + l]
+__global__ void sel_vp_norm_kernel(const float* __restrict__ score, int n, float eps, float* __restrict__ feats,
+                                   int cstride, int coff) {
+    const int l = blockIdx.x;
+    const float* s = score + (long long)l * n;
+    __shared__ double r1[32], r2[32];
+    double a = 0.0, b = 0.0;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) { const double v = s[i]; a += v; b += v * v; }
+    a = warp_sum(a); b = warp_sum(b);
+    if ((threadIdx.x & 31) == 0) { r1[threadIdx.x >> 5] = a; r2[threadIdx.x >> 5] = b; }
+    __syncthreads();
+    a = 0.0; b = 0.0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) { a += r1[w]; b += r2[w]; }
+    const double mean = a / n;
+    double var = b / n - mean * mean;
+    var = var < 0.0 ? 0.0 : var;
+    const float rstd = (float)(1.0 / sqrt(var + (double)eps));
+    const float fm = (float)mean;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) feats[(long long)i * cstride + coff + l] = (s[i] - fm) * rstd;
+}
+
+__global__ void sel_max_angle_add_kernel(const float* __restrict__ x, const float* __restrict__ embed,
+                                         float* __restrict__ out, int rfn, int an, int C) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (long long)rfn * C) return;
+    const int c = (int)(i % C);
+    const int r = (int)(i / C);
+    float m = -INFINITY;
+    for (int a = 0; a < an; ++a) m = fmaxf(m, x[((long long)r * an + a) * C + c]);
+    out[i] = m + embed[i];
+}
+
+// attention: one block per (query token i, head h); channel c = d*heads + h.
+// scores over keys in shared memory, softmax, then the weighted value sum.
+__global__ void attention_kernel(const float* __restrict__ q, const float* __restrict__ k, const float* __restrict__ v,
+                                 float* __restrict__ out, int n, int C, int heads) {
+    extern __shared__ float sh[];  // [n] probabilities + [D] query
+    const int i = blockIdx.x, h = blockIdx.y;
+    const int D = C / heads;
+    float* prob = sh;
+    float* qv = sh + n;
+    for (int d = threadIdx.x; d < D; d += blockDim.x) qv[d] = q[(long long)i * C + d * heads + h];
+    __syncthreads();
+    const float inv = rsqrtf((float)D);
+    for (int j = threadIdx.x; j < n; j += blockDim.x) {
+        float s = 0.f;
+        for (int d = 0; d < D; ++d) s = fmaf(qv[d], k[(long long)j * C + d * heads + h], s);
+        prob[j] = s * inv;
+    }
+    __syncthreads();
+    __shared__ float red[32];
+    float m = -INFINITY;
+    for (int j = threadIdx.x; j < n; j += blockDim.x) m = fmaxf(m, prob[j]);
+    m = warp_max(m);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
+    __syncthreads();
+    m = red[0];
+    for (int w = 1; w < (int)(blockDim.x >> 5); ++w) m = fmaxf(m, red[w]);
+    __syncthreads();
+    float sum = 0.f;
+    for (int j = threadIdx.x; j < n; j += blockDim.x) { const float e = expf(prob[j] - m); prob[j] = e; sum += e; }
+    sum = warp_sum(sum);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = sum;
+    __syncthreads();
+    sum = 0.f;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) sum += red[w];
+    for (int d = threadIdx.x; d < D; d += blockDim.x) {
+        float acc = 0.f;
+        for (int j = 0; j < n; ++j) acc = fmaf(prob[j], v[(long long)j * C + d * heads + h], acc);
+        out[(long long)i * C + d * heads + h] = acc / sum;
+    }
+}
+
+__global__ void layernorm_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
+                                 const float* __restrict__ beta, float* __restrict__ out, int rows, int C, float eps) {
+    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= rows) return;
+    const int lane = threadIdx.x & 31;
+    const float* xr = x + (long long)row * C;
+    float s = 0.f;
+    for (int c = lane; c < C; c += 32) s += xr[c];
+    const float mean = warp_sum(s) / (float)C;
+    float v = 0.f;
+    for (int c = lane; c < C; c += 32) { const float d = xr[c] - mean; v = fmaf(d, d, v); }
+    const float rstd = rsqrtf(warp_sum(v) / (float)C + eps);
+    for (int c = lane; c < C; c += 32) out[(long long)row * C + c] = (xr[c] - mean) * rstd * gamma[c] + beta[c];
+}
+
+__global__ void sel_parse_kernel(const float* __restrict__ logits, const float* __restrict__ angles, int rfn,
+                                 long long* __restrict__ out_idx, float* __restrict__ out) {
+    const int qi = blockIdx.x;
+    if (threadIdx.x != 0) return;
+    const float* l = logits + (long long)qi * rfn;
+    int best = 0;
+    float bv = l[0];
+    for (int r = 1; r < rfn; ++r)
+        if (l[r] > bv) { bv = l[r]; best = r; }
+    out_idx[qi] = best;
+    out[qi * 2 + 0] = angles[(long long)qi * rfn + best];
+    out[qi * 2 + 1] = bv;
+}
+
+}  // namespace g6d
+
+using namespace g6d;
+
+extern "C" int g6d_sel_corr_score(const float* ref, const float* q, int S, int P, int C, float* score,
+                                  g6d_stream_t stream) {
+    G6D_REQUIRE(ref && q && score && S > 0 && P > 0, "g6d_sel_corr_score: bad args");
+    G6D_REQUIRE(C == 512 || C == 256 || C == 128, "g6d_sel_corr_score: C must be 128, 256 or 512 (got %d)", C);
+    G6D_REQUIRE(P <= 8192, "g6d_sel_corr_score: P too large");
+    const int grid = S < 8 * kNumSMs ? S : 8 * kNumSMs;
+    const size_t smem = sizeof(float) * P;
+    cudaStream_t st = as_stream(stream);
+    if (C == 512) sel_corr_score_kernel<512><<<grid, 256, smem, st>>>(ref, q, S, P, score);
+    else if (C == 256) sel_corr_score_kernel<256><<<grid, 256, smem, st>>>(ref, q, S, P, score);
+    else sel_corr_score_kernel<128><<<grid, 256, smem, st>>>(ref, q, S, P, score);
+    G6D_CHECK_LAUNCH("g6d_sel_corr_score");
+    return G6D_OK;
+}
+
+extern "C" int g6d_sel_ref_sums(const float* ref, int S, int P, int C, double* sum1, double* sum2,
+                                g6d_stream_t stream) {
+    G6D_REQUIRE(ref && sum1 && sum2 && S > 0 && P > 0 && C > 0, "g6d_sel_ref_sums: bad args");
+    const long long PC = (long long)P * C;
+    cudaStream_t st = as_stream(stream);
+    cudaError_t e = cudaMemsetAsync(sum1, 0, sizeof(double) * PC, st);
+    if (e == cudaSuccess) e = cudaMemsetAsync(sum2, 0, sizeof(double) * PC, st);
+    if (e != cudaSuccess) { set_error("g6d_sel_ref_sums: memset failed: %s", cudaGetErrorString(e)); return G6D_ECUDA; }
+    const int s_chunk = 16;
+    dim3 grid(ceil_div(PC, 256), ceil_div(S, s_chunk));
+    sel_ref_sums_kernel<<<grid, 256, 0, st>>>(ref, S, PC, s_chunk, sum1, sum2);
+    G6D_CHECK_LAUNCH("g6d_sel_ref_sums");
+    return G6D_OK;
+}
+
+extern "C" int g6d_sel_corr_prologue(const float* q, const double* sum1, const double* sum2, int S, int P, int C,
+                                     float eps, float* scale, float* shift, g6d_stream_t stream) {
+    G6D_REQUIRE(q && sum1 && sum2 && scale && shift && S > 0 && P > 0 && C > 0, "g6d_sel_corr_prologue: bad args");
+    sel_corr_prologue_kernel<<<ceil_div(C, 32), 256, 0, as_stream(stream)>>>(q, sum1, sum2, S, P, C, eps, scale, shift);
+    G6D_CHECK_LAUNCH("g6d_sel_corr_prologue");
+    return G6D_OK;
+}
+
+extern "C" int g6d_sel_vp_norm(const float* score, int L, int n, float eps, float* feats, int cstride, int coff,
+                               g6d_stream_t stream) {
+    G6D_REQUIRE(score && feats && L > 0 && n > 0 && coff + L <= cstride, "g6d_sel_vp_norm: bad args");
+    sel_vp_norm_kernel<<<L, 256, 0, as_stream(stream)>>>(score, n, eps, feats, cstride, coff);
+    G6D_CHECK_LAUNCH("g6d_sel_vp_norm");
+    return G6D_OK;
+}
+
+extern "C" int g6d_sel_max_angle_add(const float* x, const float* embed, float* out, int rfn, int an, int C,
+                                     g6d_stream_t stream) {
+    G6D_REQUIRE(x && embed && out && rfn > 0 && an > 0 && C > 0, "g6d_sel_max_angle_add: bad args");
+    sel_max_angle_add_kernel<<<ceil_div((long long)rfn * C, 256), 256, 0, as_stream(stream)>>>(x, embed, out, rfn, an, C);
+    G6D_CHECK_LAUNCH("g6d_sel_max_angle_add");
+    return G6D_OK;
+}
+
+extern "C" int g6d_attention(const float* q, const float* k, const float* v, float* out, int n, int C, int heads,
+                             g6d_stream_t stream) {
+    G6D_REQUIRE(q && k && v && out && n > 0 && n <= 8192 && heads > 0 && C % heads == 0, "g6d_attention: bad args");
+    const size_t smem = sizeof(float) * (n + C / heads);
+    attention_kernel<<<dim3(n, heads), 64, smem, as_stream(stream)>>>(q, k, v, out, n, C, heads);
+    G6D_CHECK_LAUNCH("g6d_attention");
+    return G6D_OK;
+}
+
+extern "C" int g6d_layernorm(const float* x, const float* gamma, const float* beta, float* out, int rows, int C,
+                             float eps, g6d_stream_t stream) {
+    G6D_REQUIRE(x && gamma && beta && out && rows > 0 && C > 0, "g6d_layernorm: bad args");
+    layernorm_kernel<<<ceil_div(rows, 4), 128, 0, as_stream(stream)>>>(x, gamma, beta, out, rows, C, eps);
+    G6D_CHECK_LAUNCH("g6d_layernorm");
+    return G6D_OK;
+}
+
+extern "C" int g6d_sel_parse(const float* logits, const float* angles, int qn, int rfn, long long* out_idx, float* out,
+                             g6d_stream_t stream) {
+    G6D_REQUIRE(logits && angles && out_idx && out && qn > 0 && rfn > 0, "g6d_sel_parse: bad args");
+    sel_parse_kernel<<<qn, 32, 0, as_stream(stream)>>>(logits, angles, rfn, out_idx, out);
+    G6D_CHECK_LAUNCH("g6d_sel_parse");
+    return G6D_OK;
+}

@@ -1,0 +1,52 @@
+"""Common plumbing of the three network classes: lazily packed weights and numpy <-> device IO."""
+import numpy as np
+import torch
+import torch.nn as nn
+
+from .. import ops
+
+
+class PackedModule(nn.Module):
+    """nn.Module whose parameters are re-packed for the kernels on first use and whenever the
+    parameters change (load_state_dict, .cuda(), .to())."""
+
+    def __init__(self):
+        super().__init__()
+        self._packed = None
+        self.register_load_state_dict_post_hook(lambda module, keys: module.invalidate_packed())
+
+    def invalidate_packed(self):
+        self._packed = None
+
+    def _apply(self, fn, *args, **kwargs):
+        self._packed = None
+        return super()._apply(fn, *args, **kwargs)
+
+    @property
+    def device(self):
+        return next(self.parameters()).device
+
+    def packed(self):
+        if self._packed is None:
+            ops.require_cuda()
+            if self.device.type != 'cuda':
+                raise RuntimeError(f'{type(self).__name__}: parameters are on {self.device}; call .cuda() first '
+                                   '(the Gen6D hot path has no CPU fallback)')
+            with torch.no_grad():
+                self._packed = self._pack()
+        return self._packed
+
+    def _pack(self):
+        raise NotImplementedError
+
+    def _to_dev(self, array, dtype=None):
+        t = torch.from_numpy(np.ascontiguousarray(array))
+        if dtype is not None:
+            t = t.to(dtype)
+        return t.to(self.device, non_blocking=True)
+
+
+def linear_as_conv(weight, bias, cin_pad=None):
+    """nn.Linear / Conv1d(k=1) / Conv2d(k=1) weight -> PackedConv of a 1x1 convolution."""
+    w = weight.reshape(weight.shape[0], weight.shape[1], 1)
+    return ops.pack_conv(w, bias, stride=1, pad=0, cin_pad=cin_pad)

@@ -1,11 +1,228 @@
-import torch.nn as nn
-from .params import VGG11BNParams, selector_modules
+"""Viewpoint selector on the sm_100a kernels.  Mirrors network/selector.py (+ attention.py) of the
+reference: class name, cfg keys, checkpoint keys, load_ref_imgs / select_que_imgs numpy API and
+extract_ref_feats / compute_view_point_feats / forward tensor API.
 
-class ViewpointSelector(nn.Module):
+Device-side data layout: the cached reference stack is channels-last and
+slice-major, ref[l] = [S = rfn*an (r-major, a-minor), h_l, w_l, 512], which is simultaneously
+ * the streaming operand of the correlation-score kernel (one 2 KB row per (slice, location)),
+ * the input tensor of the first tower convolution, whose loader forms the (never
+   materialised) correlation volume q (.) ref with the first InstanceNorm3d folded in.
+"""
+import numpy as np
+import torch
+
+from .. import ops
+from .backbone import pack_vgg, vgg_v1
+from .base import PackedModule, linear_as_conv
+from .params import SEL_TOWER_POST, SEL_TOWERS, VGG11BNParams, selector_modules
+
+IN_EPS = 1e-5
+FEAT_PAD = 516  # 512 correlation features + 3 similarity scores, padded to a multiple of 4
+
+
+class ViewpointSelector(PackedModule):
     default_cfg = {'selector_angle_num': 5}
+
     def __init__(self, cfg):
         self.cfg = {**self.default_cfg, **cfg}
         super().__init__()
         self.backbone = VGG11BNParams()
-        for k, m in selector_modules(self.cfg['selector_angle_num']).items():
-            setattr(self, k, m)
+        for name, mod in selector_modules(self.cfg['selector_angle_num']).items():
+            setattr(self, name, mod)
+        self.ref_feats_cache = None   # 3 x [S, h, w, 512]
+        self.ref_sums = None          # per level (sum, sum of squares) over S, float64 [h*w, 512]
+        self.ref_pose_embed = None    # [rfn, 512]
+        self.ref_shape = None         # (rfn, an)
+
+    # ------------------------------------------------------------------ weights
+    def _pack(self):
+        an = self.cfg['selector_angle_num']
+        p = {'vgg': pack_vgg(self.backbone)}
+        p['towers'] = []
+        for lvl in range(3):
+            tower = self.corr_conv_list[lvl]
+            p['towers'].append([(ops.pack_conv(tower[s].weight, tower[s].bias, pad=(0, 1, 1)), SEL_TOWER_POST[lvl][s])
+                                for s in sorted(SEL_TOWERS[lvl])])
+        cf = self.corr_feats_conv
+        p['cf0'] = ops.pack_conv(cf[0].weight, cf[0].bias, pad=0)
+        p['cf3'] = ops.pack_conv(cf[3].weight, cf[3].bias, pad=0)
+        sp = self.score_process
+        p['sp0'] = ops.pack_conv(sp[0].weight, sp[0].bias, pad=0, cin_pad=FEAT_PAD)
+        p['sp2'] = ops.pack_conv(sp[2].weight, sp[2].bias, pad=0)
+        p['atts'] = []
+        for att in self.atts:
+            p['atts'].append({k: linear_as_conv(getattr(att, k).weight, getattr(att, k).bias)
+                              for k in ('conv_query', 'conv_key', 'conv_feats', 'conv_merge')} |
+                             {'ln_w': att.norm.norm.weight.float().contiguous(),
+                              'ln_b': att.norm.norm.bias.float().contiguous()})
+        p['mlps'] = [(linear_as_conv(m[0].weight, m[0].bias), linear_as_conv(m[3].weight, m[3].bias)) for m in self.mlps]
+        p['score_predict'] = [linear_as_conv(self.score_predict[i].weight, self.score_predict[i].bias) for i in (0, 2)]
+        # angle_predict consumes feats.permute(0,1,3,2).reshape(qn, f*an, rfn): channel = f*an + a
+        # (selector.py:212-214).  Our per-reference row is [an, FEAT_PAD] flattened (a*FEAT_PAD + f),
+        # so permute (and zero-pad) the first layer's input columns once here.
+        w0 = self.angle_predict[0].weight.reshape(512, 515, an)            # [o, f, a]
+        w0p = torch.zeros(512, an, FEAT_PAD, device=w0.device, dtype=torch.float32)
+        w0p[:, :, :515] = w0.permute(0, 2, 1)
+        p['angle_predict'] = [linear_as_conv(w0p.reshape(512, an * FEAT_PAD, 1), self.angle_predict[0].bias)] + \
+                             [linear_as_conv(self.angle_predict[i].weight, self.angle_predict[i].bias) for i in (2, 4)]
+        p['vpe'] = [linear_as_conv(self.view_point_encoder[i].weight, self.view_point_encoder[i].bias) for i in (0, 2, 4)]
+        return p
+
+    # ------------------------------------------------------------------ features
+    def _feats(self, imgs_norm4):
+        """selector.py:113-119: VGG + per-pixel L2 normalisation; input already ImageNet-normalised."""
+        return [ops.l2norm_channels(f) for f in vgg_v1(self.packed()['vgg'], imgs_norm4)]
+
+    @staticmethod
+    def viewpoints(ref_poses, object_center, object_vert):
+        """Normalised viewpoint directions (selector.py:131-147), fp32 on the host: camera centres
+        relative to the object in the (x, y, vert) frame anchored on the FIRST reference."""
+        ref_poses = torch.as_tensor(ref_poses, dtype=torch.float32).cpu()
+        center = torch.as_tensor(object_center, dtype=torch.float32).cpu()
+        vert = torch.as_tensor(object_vert, dtype=torch.float32).cpu()
+        cam = (-ref_poses[:, :3, :3].permute(0, 2, 1) @ ref_poses[:, :3, 3:])[..., 0] - center[None]
+        fwd = cam[0]
+        y = torch.linalg.cross(vert, fwd)
+        x = torch.linalg.cross(y, vert)
+        nrm = lambda v: v / torch.clamp(torch.linalg.norm(v), min=1e-12)
+        R = torch.stack([nrm(x), nrm(y), nrm(vert)], 0)
+        cam = cam @ R.T
+        return cam / torch.clamp(torch.linalg.norm(cam, dim=1, keepdim=True), min=1e-12)
+
+    def _load_nhwc(self, ref_norm4, rfn, an, ref_poses, object_center, object_vert, chunk=64):
+        """ref_norm4: [S = rfn*an (r-major), h, w, 4] ImageNet-normalised (selector.py:121-148)."""
+        p = self.packed()
+        S = rfn * an
+        levels = [[], [], []]
+        for s0 in range(0, S, chunk):
+            for l, f in enumerate(self._feats(ref_norm4[s0:s0 + chunk])):
+                levels[l].append(f)
+        self.ref_feats_cache = [torch.cat(lv, 0) if len(lv) > 1 else lv[0] for lv in levels]
+        self.ref_sums = [ops.sel_ref_sums(f.reshape(S, -1, f.shape[-1])) for f in self.ref_feats_cache]
+        self.ref_shape = (rfn, an)
+        vp = torch.zeros(rfn, 4, dtype=torch.float32)
+        vp[:, :3] = self.viewpoints(ref_poses, object_center, object_vert)
+        x = vp.to(self.device).reshape(rfn, 1, 1, 4)
+        for i, pc in enumerate(p['vpe']):
+            x = ops.conv(x, pc, act=ops.ACT_RELU if i < 2 else ops.ACT_NONE)
+        self.ref_pose_embed = x.reshape(rfn, 512)
+
+    def _tower(self, level, ref, scale, shift, cat_buf, S):
+        """corr_conv_list[level] (selector.py:27-69) on the implicit correlation volume."""
+        convs = self.packed()['towers'][level]
+        x, pro, ps, pb = ref, ops.PRO_CORR, scale, shift
+        for i, (pc, post) in enumerate(convs):
+            last = i + 1 == len(convs)
+            y = ops.conv(x, pc, prologue=pro, pro_scale=ps, pro_shift=pb, group_rows=S,
+                         out=cat_buf if last else None, out_coff=256 * level if last else 0)
+            if last:
+                break
+            # InstanceNorm3d statistics over (S, h, w) of the raw conv output; the normalisation
+            # itself (and the ReLU) is applied by the next conv's loader.  MaxPool commutes with
+            # the positive-slope affine, so pooling the raw tensor first is exact.
+            ps, pb = ops.instnorm_stats(y, rows_per_group=y.numel() // y.shape[-1], eps=IN_EPS)
+            pro = ops.PRO_AFFINE_RELU if 'r' in post else ops.PRO_AFFINE
+            x = ops.maxpool2x2(y) if 'p' in post else y
+
+    def _select_one(self, q_feats):
+        """selector.py:177-215 for one query.  q_feats: 3 x [h, w, 512].  -> logits [rfn], angles [rfn]"""
+        p = self.packed()
+        rfn, an = self.ref_shape
+        S = rfn * an
+        dev = self.device
+        cat_buf = torch.empty(S, 4, 4, 768, device=dev, dtype=torch.float32)
+        feats = torch.zeros(S, FEAT_PAD, device=dev, dtype=torch.float32)
+        scores = torch.empty(3, S, device=dev, dtype=torch.float32)
+        for l, (q, ref, (s1, s2)) in enumerate(zip(q_feats, self.ref_feats_cache, self.ref_sums)):
+            h, w, c = q.shape
+            q2 = q.reshape(h * w, c)
+            ops.sel_corr_score(ref.reshape(S, h * w, c), q2, out=scores[l])
+            scale, shift = ops.sel_corr_prologue(q2, s1, s2, S, IN_EPS)
+            self._tower(l, ref, scale, shift, cat_buf, S)
+        # corr_feats_conv (selector.py:71-77): 1x1 768->512, IN, ReLU, 1x1 512->512, AvgPool(4,4).
+        # The second 1x1 conv is linear, so the 4x4 average is taken first (16x less work).
+        y = ops.conv(cat_buf, p['cf0'])
+        ps, pb = ops.instnorm_stats(y, rows_per_group=S * 16, eps=IN_EPS)
+        y = ops.avgpool_affine(y.reshape(S * 16, 512), 16, ps, pb, rows_per_group=S * 16, act=ops.ACT_RELU)
+        ops.conv(y.reshape(S, 1, 1, 512), p['cf3'], out=feats.reshape(S, 1, 1, FEAT_PAD), out_coff=0)
+        ops.sel_vp_norm(scores, feats, 512, IN_EPS)                     # vp_norm, selector.py:201
+        x = ops.conv(feats.reshape(S, 1, 1, FEAT_PAD), p['sp0'], act=ops.ACT_RELU)
+        x = ops.conv(x, p['sp2']).reshape(rfn, an, 512)
+        sf = ops.sel_max_angle_add(x, self.ref_pose_embed)              # selector.py:203-204
+        for att, (m0, m3) in zip(p['atts'], p['mlps']):
+            x4 = sf.reshape(rfn, 1, 1, 512)
+            qv = ops.conv(x4, att['conv_query']).reshape(rfn, 512)
+            kv = ops.conv(x4, att['conv_key']).reshape(rfn, 512)
+            vv = ops.conv(x4, att['conv_feats']).reshape(rfn, 512)
+            msg = ops.attention(qv, kv, vv, heads=8)
+            msg = ops.conv(msg.reshape(rfn, 1, 1, 512), att['conv_merge']).reshape(rfn, 512)
+            msg = ops.layernorm(msg, att['ln_w'], att['ln_b'], 1e-5)
+            y = ops.conv(torch.cat([sf, msg], 1).reshape(rfn, 1, 1, 1024), m0)
+            ps, pb = ops.instnorm_stats(y, rows_per_group=rfn, eps=IN_EPS)      # InstanceNorm1d over rfn
+            y = ops.conv(y, m3, prologue=ops.PRO_AFFINE_RELU, pro_scale=ps, pro_shift=pb, group_rows=rfn)
+            ps, pb = ops.instnorm_stats(y, rows_per_group=rfn, eps=IN_EPS)
+            y = ops.affine_act(y.reshape(rfn, 512), ps, pb, rows_per_group=rfn, act=ops.ACT_RELU)
+            sf = ops.add(y, sf)
+        x = ops.conv(sf.reshape(rfn, 1, 1, 512), p['score_predict'][0], act=ops.ACT_RELU)
+        logits = ops.conv(x, p['score_predict'][1]).reshape(rfn)
+        x = feats.reshape(rfn, 1, 1, an * FEAT_PAD)
+        for i, pc in enumerate(p['angle_predict']):
+            x = ops.conv(x, pc, act=ops.ACT_RELU if i < 2 else ops.ACT_NONE)
+        return logits, x.reshape(rfn), scores
+
+    def _select_nhwc(self, que_norm4):
+        if self.ref_feats_cache is None:
+            raise RuntimeError('ViewpointSelector: load_ref_imgs / extract_ref_feats must be called first')
+        feats = self._feats(que_norm4)
+        logits, angles, taps = [], [], []
+        for qi in range(que_norm4.shape[0]):
+            lg, ang, sc = self._select_one([f[qi] for f in feats])
+            logits.append(lg)
+            angles.append(ang)
+            taps.append(sc)
+        return torch.stack(logits, 0), torch.stack(angles, 0), torch.stack(taps, 0)
+
+    # ------------------------------------------------------------------ reference tensor API
+    def extract_ref_feats(self, ref_imgs, ref_poses, object_center, object_vert, is_train=False):
+        """ref_imgs [an,rfn,3,h,w] in [0,1] (selector.py:121-148; is_train=False path only)."""
+        if is_train:
+            raise NotImplementedError('inference-only build: random forward-view selection is a training feature')
+        with torch.no_grad():
+            an, rfn, _, h, w = ref_imgs.shape
+            x = ref_imgs.permute(1, 0, 2, 3, 4).reshape(rfn * an, 3, h, w).float().contiguous()
+            x = ops.imagenet_norm(ops.nchw_to_nhwc(x), out_c=4)
+            self._load_nhwc(x, rfn, an, ref_poses, object_center, object_vert)
+
+    def compute_view_point_feats(self, que_imgs):
+        """que_imgs [qn,3,h,w] in [0,1] -> logits [qn,rfn], angles [qn,rfn] (selector.py:177-215)."""
+        with torch.no_grad():
+            x = ops.imagenet_norm(ops.nchw_to_nhwc(que_imgs.float().contiguous()), out_c=4)
+            logits, angles, _ = self._select_nhwc(x)
+        return logits, angles
+
+    def forward(self, data):
+        self.extract_ref_feats(data['ref_imgs'], data['ref_imgs_info']['poses'], data['object_center'],
+                               data['object_vert'], 'eval' not in data)
+        logits, angles = self.compute_view_point_feats(data['que_imgs_info']['imgs'])
+        return {'ref_vp_logits': logits, 'angles_pr': angles}
+
+    # ------------------------------------------------------------------ reference numpy API
+    def load_ref_imgs(self, ref_imgs, ref_poses, object_center, object_vert):
+        """@param ref_imgs: uint8 [an,rfn,h,w,3]; ref_poses [rfn,3,4]; object_center [3]; object_vert [3]
+        (selector.py:150-163)"""
+        with torch.no_grad():
+            an, rfn, h, w, _ = ref_imgs.shape
+            u8 = self._to_dev(np.ascontiguousarray(ref_imgs.transpose(1, 0, 2, 3, 4))).reshape(rfn * an, h, w, 3)
+            x = ops.preprocess_u8(u8, out_c=4, imagenet_norm=True)
+            self._load_nhwc(x, rfn, an, ref_poses.astype(np.float32), object_center.astype(np.float32),
+                            object_vert.astype(np.float32))
+
+    def select_que_imgs(self, que_imgs):
+        """@param que_imgs: uint8 [qn,h,w,3] -> {'ref_idx': i64 [qn], 'angles': f32 [qn], 'scores': f32 [qn,rfn]}
+        (selector.py:165-175; the angle is returned un-rescaled, as the reference does)"""
+        with torch.no_grad():
+            x = ops.preprocess_u8(self._to_dev(que_imgs), out_c=4, imagenet_norm=True)
+            logits, angles, _ = self._select_nhwc(x)
+            idx, out = ops.sel_parse(logits, angles)
+            idx, out, logits = idx.cpu().numpy(), out.cpu().numpy(), logits.cpu().numpy()
+        return {'ref_idx': idx, 'angles': out[:, 0].copy(), 'scores': logits}

@@ -1,0 +1,322 @@
+"""Torch-tensor front end of the C ABI.
+
+PyTorch is used here only as the device-memory allocator and stream provider: every function
+checks its tensors (CUDA, contiguous, dtype), takes raw pointers and calls into
+libgen6d_b200.so on torch's current stream.  Activations are fp32 channels-last.
+"""
+import ctypes as C
+from dataclasses import dataclass
+from typing import Optional
+
+import torch
+
+from . import _lib
+from ._lib import ACT_LEAKY01, ACT_NONE, ACT_RELU, PRO_AFFINE, PRO_AFFINE_RELU, PRO_CORR, PRO_NONE  # noqa: F401
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _p(t, dtype=torch.float32):
+    if t is None:
+        return None
+    if not (t.is_cuda and t.dtype == dtype and t.is_contiguous()):
+        raise ValueError(f'expected a contiguous CUDA {dtype} tensor, got {t.dtype} {t.device} '
+                         f'contiguous={t.is_contiguous()} shape={tuple(t.shape)}')
+    return C.c_void_p(t.data_ptr())
+
+
+def _call(name, *args):
+    _lib.check(getattr(_lib.lib(), name)(*args), name)
+
+
+def require_cuda():
+    if not torch.cuda.is_available():
+        raise _lib.Gen6DLibraryError('no CUDA device: the Gen6D hot path has no CPU fallback')
+    _lib.lib()
+
+
+# ------------------------------------------------------------------------------- layout / images
+def preprocess_u8(img, out_c=4, imagenet_norm=True):
+    """u8 [..., H, W, 3] -> f32 [..., H, W, out_c]: /255 (+ ImageNet normalisation)."""
+    out = torch.empty(*img.shape[:-1], out_c, device=img.device, dtype=torch.float32)
+    _call('g6d_preprocess_u8', _p(img, torch.uint8), _p(out), img.numel() // 3, out_c, int(imagenet_norm), _stream())
+    return out
+
+
+def imagenet_norm(x, out_c=4):
+    out = torch.empty(*x.shape[:-1], out_c, device=x.device, dtype=torch.float32)
+    _call('g6d_imagenet_norm', _p(x), _p(out), x.numel() // x.shape[-1], x.shape[-1], out_c, _stream())
+    return out
+
+
+def nchw_to_nhwc(x, out_c=None):
+    N, Cc, H, W = x.shape
+    out_c = out_c or Cc
+    out = torch.empty(N, H, W, out_c, device=x.device, dtype=torch.float32)
+    _call('g6d_nchw_to_nhwc', _p(x), _p(out), N, Cc, H, W, out_c, _stream())
+    return out
+
+
+def nhwc_to_nchw(x, channels=None):
+    N, H, W, cs = x.shape
+    Cc = channels or cs
+    out = torch.empty(N, Cc, H, W, device=x.device, dtype=torch.float32)
+    _call('g6d_nhwc_to_nchw', _p(x), _p(out), N, Cc, H, W, cs, _stream())
+    return out
+
+
+def resize_bilinear(x, Ho, Wo, out=None, out_coff=0):
+    N, Hi, Wi, Cc = x.shape
+    if out is None:
+        out = torch.empty(N, Ho, Wo, Cc, device=x.device, dtype=torch.float32)
+    _call('g6d_resize_bilinear', _p(x), _p(out), N, Hi, Wi, Ho, Wo, Cc, out.shape[-1], out_coff, _stream())
+    return out
+
+
+def resize_nearest(x, Ho, Wo):
+    N, Hi, Wi, Cc = x.shape
+    out = torch.empty(N, Ho, Wo, Cc, device=x.device, dtype=torch.float32)
+    _call('g6d_resize_nearest', _p(x), _p(out), N, Hi, Wi, Ho, Wo, Cc, _stream())
+    return out
+
+
+def maxpool2x2(x):
+    N, H, W, Cc = x.shape
+    out = torch.empty(N, H // 2, W // 2, Cc, device=x.device, dtype=torch.float32)
+    _call('g6d_maxpool2x2', _p(x), _p(out), N, H, W, Cc, _stream())
+    return out
+
+
+def l2norm_channels(x, eps=1e-12):
+    out = torch.empty_like(x)
+    _call('g6d_l2norm_channels', _p(x), _p(out), x.numel() // x.shape[-1], x.shape[-1], eps, _stream())
+    return out
+
+
+def instnorm_stats(x, rows_per_group, channels=None, coff=0, eps=1e-5):
+    """x [..., cstride]; statistics over groups of `rows_per_group` consecutive rows.
+    Returns (scale, shift), each [groups, C]: InstanceNorm(x) == x*scale + shift."""
+    cstride = x.shape[-1]
+    Cc = channels or cstride
+    rows = x.numel() // cstride
+    groups = rows // rows_per_group
+    scale = torch.empty(groups, Cc, device=x.device, dtype=torch.float32)
+    shift = torch.empty_like(scale)
+    ws = torch.empty(groups * Cc * 2, device=x.device, dtype=torch.float64)
+    _call('g6d_instnorm_stats', _p(x), rows, Cc, cstride, coff, rows_per_group, eps, _p(scale), _p(shift),
+          _p(ws, torch.float64), _stream())
+    return scale, shift
+
+
+def affine_act(x, scale, shift, rows_per_group, act=ACT_NONE, channels=None, in_coff=0, out=None, out_coff=0):
+    ics = x.shape[-1]
+    Cc = channels or ics
+    rows = x.numel() // ics
+    if out is None:
+        out = torch.empty(*x.shape[:-1], Cc, device=x.device, dtype=torch.float32)
+    _call('g6d_affine_act', _p(x), _p(out), rows, Cc, rows_per_group, _p(scale), _p(shift), act, ics, in_coff,
+          out.shape[-1], out_coff, _stream())
+    return out
+
+
+def avgpool_affine(x, spatial, scale=None, shift=None, rows_per_group=1, act=ACT_NONE):
+    """x [n_out*spatial, C] -> [n_out, C]: mean over `spatial` rows of act(x*scale+shift)."""
+    Cc = x.shape[-1]
+    n_out = x.numel() // Cc // spatial
+    out = torch.empty(n_out, Cc, device=x.device, dtype=torch.float32)
+    _call('g6d_avgpool_affine', _p(x), _p(out), n_out, spatial, Cc, rows_per_group, _p(scale), _p(shift), act, _stream())
+    return out
+
+
+def add(a, b):
+    out = torch.empty_like(a)
+    _call('g6d_add', _p(a), _p(b), _p(out), a.numel(), _stream())
+    return out
+
+
+# ------------------------------------------------------------------------------- convolution
+@dataclass
+class PackedConv:
+    """Convolution weights in the library's [K, ldw] layout (+ bias), see g6d_pack_conv_weight."""
+    w: torch.Tensor
+    bias: Optional[torch.Tensor]
+    cin: int          # padded input channels the packed weight expects
+    cout: int
+    k: tuple          # (kd, kh, kw)
+    stride: int = 1
+    pad: tuple = (0, 0, 0)
+
+
+def pack_conv(weight, bias=None, stride=1, pad=None, cin_pad=None, cout_scale=None, bias_override=None):
+    """weight: reference layout [Cout, Cin, *k] (1-3 spatial dims) on the GPU."""
+    cout, cin = weight.shape[:2]
+    ks = tuple(weight.shape[2:])
+    k3 = (1,) * (3 - len(ks)) + ks
+    if pad is None:
+        pad = tuple(kk // 2 for kk in k3)
+    elif isinstance(pad, int):
+        pad = tuple(pad if kk > 1 else 0 for kk in k3)
+    else:
+        pad = (0,) * (3 - len(pad)) + tuple(pad)
+    cin_pad = cin_pad or ((cin + 3) // 4 * 4)
+    taps = k3[0] * k3[1] * k3[2]
+    ldw = (cout + 3) // 4 * 4
+    w = weight.detach().to(torch.float32).contiguous()
+    out = torch.empty(taps * cin_pad, ldw, device=w.device, dtype=torch.float32)
+    _call('g6d_pack_conv_weight', _p(w), _p(out), cout, cin, cin_pad, taps,
+          _p(cout_scale.contiguous()) if cout_scale is not None else None, _stream())
+    b = bias_override if bias_override is not None else bias
+    b = b.detach().to(torch.float32).contiguous() if b is not None else None
+    return PackedConv(out, b, cin_pad, cout, k3, stride, pad)
+
+
+def transpose_to_packed(x2d):
+    """[rows, K] -> packed [K, ldw(rows)] weights (detector reference features as kernels)."""
+    rows, cols = x2d.shape
+    out = torch.empty(cols, (rows + 3) // 4 * 4, device=x2d.device, dtype=torch.float32)
+    _call('g6d_transpose2d', _p(x2d), _p(out), rows, cols, _stream())
+    return out
+
+
+def conv(x, pc, prologue=PRO_NONE, pro_scale=None, pro_shift=None, group_rows=1, act=ACT_NONE,
+         in_coff=0, out=None, out_coff=0):
+    """x [B, D, H, W, cs] or [B, H, W, cs]; returns [B, Do, Ho, Wo, Cout] (or 4-D for 4-D input)."""
+    four = x.dim() == 4
+    if four:
+        B, H, W, cs = x.shape
+        D = 1
+    else:
+        B, D, H, W, cs = x.shape
+    kd, kh, kw = pc.k
+    pd, ph, pw = pc.pad
+    s = pc.stride
+    Do, Ho, Wo = (D + 2 * pd - kd) // s + 1, (H + 2 * ph - kh) // s + 1, (W + 2 * pw - kw) // s + 1
+    if out is None:
+        shape = (B, Ho, Wo, pc.cout) if four else (B, Do, Ho, Wo, pc.cout)
+        out = torch.empty(shape, device=x.device, dtype=torch.float32)
+    d = _lib.ConvDesc(B=B, D=D, H=H, W=W, Cin=pc.cin, in_cstride=cs, in_coff=in_coff, Cout=pc.cout, kd=kd, kh=kh,
+                      kw=kw, stride=s, pd=pd, ph=ph, pw=pw, Do=Do, Ho=Ho, Wo=Wo, out_cstride=out.shape[-1],
+                      out_coff=out_coff, prologue=prologue, group_rows=group_rows, act=act)
+    nbytes = _lib.lib().g6d_conv_workspace_bytes(C.byref(d))
+    if nbytes < 0:
+        _lib.check(-1, 'g6d_conv_workspace_bytes')
+    ws = torch.empty(nbytes // 4, device=x.device, dtype=torch.float32) if nbytes > 0 else None
+    _call('g6d_conv', C.byref(d), _p(x), _p(pc.w), _p(pc.bias), _p(pro_scale), _p(pro_shift), _p(out), _p(ws), _stream())
+    return out
+
+
+def linear_smallm(x, w, bias, act=ACT_NONE):
+    """x [M<=8, K], w [N, K] (row-major) -> [M, N]."""
+    M, K = x.shape
+    N = w.shape[0]
+    out = torch.empty(M, N, device=x.device, dtype=torch.float32)
+    _call('g6d_linear_smallm', _p(x), _p(w), _p(bias), _p(out), M, N, K, act, _stream())
+    return out
+
+
+# ------------------------------------------------------------------------------- detector
+def det_score_fuse(maps, sizes, rfn, hs, ws, stats, clip, w1, b1, w2, b2, qn):
+    """maps[s][l]: raw correlation [qn, Hl, Wl, rfn]; sizes[s][l] = (Hl, Wl). -> [qn, hs, ws, 64]."""
+    m = _lib.DetMaps()
+    m.n_scales, m.rfn, m.hs, m.ws = len(maps), rfn, hs, ws
+    for s, lv in enumerate(maps):
+        for l, t in enumerate(lv):
+            m.map[s][l] = _p(t).value
+            m.H[s][l], m.W[s][l] = sizes[s][l]
+    for l in range(3):
+        m.mu[l] = float(stats[l][0])
+        m.inv_sigma[l] = 1.0 / float(stats[l][1])
+    m.clip = float(clip)
+    out = torch.empty(qn, hs, ws, 64, device=w1.device, dtype=torch.float32)
+    _call('g6d_det_score_fuse', C.byref(m), qn, _p(w1), _p(b1), _p(w2), _p(b2), _p(out), _stream())
+    return out
+
+
+def det_parse(scores, scales, offsets, pool_ratio=8):
+    """scores/scales [qn,hs,ws,1], offsets [qn,hs,ws,2] -> (out [qn,4] = x,y,scale,score; idx [qn] int64)."""
+    qn, hs, ws, _ = scores.shape
+    out = torch.empty(qn, 4, device=scores.device, dtype=torch.float32)
+    idx = torch.empty(qn, device=scores.device, dtype=torch.int64)
+    _call('g6d_det_parse', _p(scores), _p(scales), _p(offsets), qn, hs, ws, pool_ratio, _p(out),
+          _p(idx, torch.int64), _stream())
+    return out, idx
+
+
+# ------------------------------------------------------------------------------- selector
+def sel_ref_sums(ref):
+    """ref [S, P, C] -> (sum, sum of squares) over S, float64 [P, C]."""
+    S, Pn, Cc = ref.shape
+    s1 = torch.empty(Pn, Cc, device=ref.device, dtype=torch.float64)
+    s2 = torch.empty_like(s1)
+    _call('g6d_sel_ref_sums', _p(ref), S, Pn, Cc, _p(s1, torch.float64), _p(s2, torch.float64), _stream())
+    return s1, s2
+
+
+def sel_corr_prologue(q, s1, s2, S, eps=1e-5):
+    Pn, Cc = q.shape
+    scale = torch.empty(Pn, Cc, device=q.device, dtype=torch.float32)
+    shift = torch.empty(Cc, device=q.device, dtype=torch.float32)
+    _call('g6d_sel_corr_prologue', _p(q), _p(s1, torch.float64), _p(s2, torch.float64), S, Pn, Cc, eps, _p(scale),
+          _p(shift), _stream())
+    return scale, shift
+
+
+def sel_corr_score(ref, q, out=None):
+    S, Pn, Cc = ref.shape
+    if out is None:
+        out = torch.empty(S, device=ref.device, dtype=torch.float32)
+    _call('g6d_sel_corr_score', _p(ref), _p(q), S, Pn, Cc, _p(out), _stream())
+    return out
+
+
+def sel_vp_norm(score, feats, coff, eps=1e-5):
+    Ln, n = score.shape
+    _call('g6d_sel_vp_norm', _p(score), Ln, n, eps, _p(feats), feats.shape[-1], coff, _stream())
+
+
+def sel_max_angle_add(x, embed):
+    rfn, an, Cc = x.shape
+    out = torch.empty(rfn, Cc, device=x.device, dtype=torch.float32)
+    _call('g6d_sel_max_angle_add', _p(x), _p(embed), _p(out), rfn, an, Cc, _stream())
+    return out
+
+
+def attention(q, k, v, heads):
+    n, Cc = q.shape
+    out = torch.empty_like(q)
+    _call('g6d_attention', _p(q), _p(k), _p(v), _p(out), n, Cc, heads, _stream())
+    return out
+
+
+def layernorm(x, gamma, beta, eps=1e-5):
+    rows, Cc = x.shape
+    out = torch.empty_like(x)
+    _call('g6d_layernorm', _p(x), _p(gamma), _p(beta), _p(out), rows, Cc, eps, _stream())
+    return out
+
+
+def sel_parse(logits, angles):
+    qn, rfn = logits.shape
+    idx = torch.empty(qn, device=logits.device, dtype=torch.int64)
+    out = torch.empty(qn, 2, device=logits.device, dtype=torch.float32)
+    _call('g6d_sel_parse', _p(logits), _p(angles), qn, rfn, _p(idx, torch.int64), _p(out), _stream())
+    return idx, out
+
+
+# ------------------------------------------------------------------------------- refiner
+def ref_volume_fill(ref_feats, que_feats, ref_Ks, ref_poses, que_Ks, que_poses, sn, img_h, img_w):
+    Q, R, fh, fw, Cc = ref_feats.shape
+    mean_in = torch.empty(Q, sn, sn, sn, 2 * Cc, device=ref_feats.device, dtype=torch.float32)
+    stdv = torch.empty(Q, sn, sn, sn, Cc, device=ref_feats.device, dtype=torch.float32)
+    _call('g6d_ref_volume_fill', _p(ref_feats), _p(que_feats), _p(ref_Ks), _p(ref_poses), _p(que_Ks), _p(que_poses),
+          Q, R, fh, fw, Cc, sn, img_h, img_w, _p(mean_in), _p(stdv), _stream())
+    return mean_in, stdv
+
+
+def ref_pose_heads(x, w, b):
+    M, K = x.shape
+    out = torch.empty(M, 7, device=x.device, dtype=torch.float32)
+    _call('g6d_ref_pose_heads', _p(x), _p(w), _p(b), _p(out), M, K, _stream())
+    return out

@@ -1,0 +1,206 @@
+/*
+ * gen6d_b200.h -- C ABI of libgen6d_b200.so: the sm_100a kernels behind the Gen6D inference
+ * hot path (detector correlation head, selector similarity scoring, refiner feature volume +
+ * conv stacks).
+ *
+ * The reference (liuyuan-pal/Gen6D) is pure PyTorch and has no FFI of its own;
+ * this header is the "lower face" of the drop-in boundary: the entry points that the Python
+ * classes mirroring network/{detector,selector,refiner}.py bind with ctypes.  Each entry cites
+ * the reference call site whose arithmetic it replaces.
+ *
+ * Conventions
+ *  - every function returns 0 on success, a negative G6D_E* code otherwise;
+ *    g6d_last_error() gives a thread-local message for the last failure on this thread;
+ *  - all pointers are DEVICE pointers unless the parameter is named host_*; the caller owns
+ *    every buffer (inputs, outputs, workspaces); the library never allocates device memory,
+ *    never synchronises, and only enqueues work on the `stream` it is given (so calls can be
+ *    captured into CUDA graphs);
+ *  - activations are fp32, channels-last: [B, (D,) H, W, C] with C contiguous.  The NCHW
+ *    tensors of the reference API are converted at the Python boundary with
+ *    g6d_nchw_to_nhwc / g6d_nhwc_to_nchw;
+ *  - convolution weights are packed [K, ldw] (ldw = Cout rounded up to 4) with
+ *    K = ((kz*kh + ky)*kw + kx)*Cin + c
+ *    (g6d_pack_conv_weight does this from the reference's [Cout, Cin, kd, kh, kw]).
+ */
+#ifndef GEN6D_B200_H
+#define GEN6D_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define G6D_OK 0
+#define G6D_EINVAL (-1)   /* bad argument / unsupported shape */
+#define G6D_ECUDA (-2)    /* CUDA runtime error at launch */
+
+typedef void* g6d_stream_t; /* cudaStream_t */
+
+const char* g6d_last_error(void);
+int g6d_version(void);
+/* number of kernel launches issued through this library since load (all threads) */
+long long g6d_launch_count(void);
+
+/* ------------------------------------------------------------------ layout / image ops ---- */
+/* utils/base_utils.py:117-118 color_map_forward (+ torchvision Normalize of
+ * network/detector.py:156,189 when imagenet_norm != 0).  u8 [n_pixels,3] -> f32 [n_pixels,out_c],
+ * out_c = 3 or 4 (channel 3 = 0: padding so the first VGG conv can use 128-bit loads). */
+int g6d_preprocess_u8(const uint8_t* img, float* out, long long n_pixels, int out_c, int imagenet_norm,
+                      g6d_stream_t stream);
+/* (x - mean) / std on f32 [n_pixels, in_c] -> [n_pixels, out_c] (in_c, out_c in {3,4})
+ * (network/detector.py:189, selector.py:115, refiner.py:65) */
+int g6d_imagenet_norm(const float* in, float* out, long long n_pixels, int in_c, int out_c, g6d_stream_t stream);
+/* NCHW [N,C,H,W] -> channels-last [N,H,W,out_c] (channels >= C zero) and back */
+int g6d_nchw_to_nhwc(const float* in, float* out, int N, int C, int H, int W, int out_c, g6d_stream_t stream);
+int g6d_nhwc_to_nchw(const float* in, float* out, int N, int C, int H, int W, int in_c, g6d_stream_t stream);
+/* F.interpolate(mode='bilinear', align_corners=False) on channels-last data
+ * (network/detector.py:240,243; network/refiner.py:75-76).  Output rows have `out_cstride`
+ * channels and the C results land at channel offset `out_coff` (writes into concat buffers). */
+int g6d_resize_bilinear(const float* in, float* out, int N, int Hi, int Wi, int Ho, int Wo, int C,
+                        int out_cstride, int out_coff, g6d_stream_t stream);
+/* F.interpolate default (nearest): src = floor(dst * in / out) (network/detector.py:201) */
+int g6d_resize_nearest(const float* in, float* out, int N, int Hi, int Wi, int Ho, int Wo, int C, g6d_stream_t stream);
+/* MaxPool 2x2 stride 2 over (H, W) (VGG 'M' layers; selector MaxPool3d((1,2,2))) */
+int g6d_maxpool2x2(const float* in, float* out, int N, int H, int W, int C, g6d_stream_t stream);
+/* F.normalize(dim=1) == x / max(||x||_2, eps) over the channel axis of each row
+ * (network/selector.py:118, network/refiner.py:69-71) */
+int g6d_l2norm_channels(const float* in, float* out, long long rows, int C, float eps, g6d_stream_t stream);
+/* y = act(x * scale[g,c] + shift[g,c]); rows_per_group consecutive rows share a group.
+ * act: 0 none, 1 ReLU.  Materialises an InstanceNorm (+ReLU) where a consumer needs it.
+ * Input rows have `in_cstride` channels (C taken from offset in_coff); same for output. */
+int g6d_affine_act(const float* in, float* out, long long rows, int C, long long rows_per_group,
+                   const float* scale, const float* shift, int act,
+                   int in_cstride, int in_coff, int out_cstride, int out_coff, g6d_stream_t stream);
+/* mean over `spatial` consecutive rows of act(x*scale+shift) -> [groups_of_rows, C]
+ * (AvgPool3d((1,4,4)) of network/selector.py:76 applied after the fused IN+ReLU). */
+int g6d_avgpool_affine(const float* in, float* out, long long n_out, int spatial, int C, long long rows_per_group,
+                       const float* scale, const float* shift, int act, g6d_stream_t stream);
+int g6d_add(const float* a, const float* b, float* out, long long n, g6d_stream_t stream);
+
+/* ------------------------------------------------------------------ instance-norm stats ---- */
+/* InstanceNorm{1,2,3}d(affine=False, eps) statistics (biased variance) of a channels-last
+ * tensor: `rows` rows of C channels (taken at channel offset `coff` of rows `cstride` wide),
+ * `rows_per_group` consecutive rows form one (sample, *) group.  Writes scale = rstd and
+ * shift = -mean*rstd, each [groups, C], for consumption by prologues / g6d_affine_act.
+ * ws: 2*groups*C doubles of workspace.  (network/selector.py:27-87, refiner.py:18-22,82-86) */
+int g6d_instnorm_stats(const float* x, long long rows, int C, int cstride, int coff, long long rows_per_group,
+                       float eps, float* scale, float* shift, double* ws, g6d_stream_t stream);
+
+/* ------------------------------------------------------------------ convolution ------------ */
+typedef struct g6d_conv_desc {
+    int B, D, H, W, Cin;      /* input [B,D,H,W,*]; channels [in_coff, in_coff+Cin) of rows in_cstride wide */
+    int in_cstride, in_coff;
+    int Cout, kd, kh, kw;
+    int stride;               /* same in all spatial dims that have k>1 */
+    int pd, ph, pw;           /* zero padding */
+    int Do, Ho, Wo;           /* output dims (validated) */
+    int out_cstride, out_coff;
+    int prologue;             /* G6D_PRO_* applied to in-bounds input elements before the MAC */
+    long long group_rows;     /* G6D_PRO_AFFINE*: input batch items per norm group */
+    int act;                  /* G6D_ACT_* epilogue after bias */
+} g6d_conv_desc;
+
+#define G6D_PRO_NONE 0
+#define G6D_PRO_AFFINE 1        /* x*scale[g,c] + shift[g,c]          (folded InstanceNorm)        */
+#define G6D_PRO_AFFINE_RELU 2   /* relu(x*scale[g,c] + shift[g,c])    (folded InstanceNorm + ReLU) */
+#define G6D_PRO_CORR 3          /* x*scale[pos,c] + shift[c]: selector correlation volume
+                                   q (.) ref with the first InstanceNorm3d folded in            */
+#define G6D_ACT_NONE 0
+#define G6D_ACT_RELU 1
+#define G6D_ACT_LEAKY01 2
+
+/* Implicit-GEMM convolution (1x1 ... 3x3x3, stride 1/2) with fused prologue/bias/activation.
+ * Replaces F.conv2d / Conv3d call sites: VGG (pretrain_models.py:17-31), detector correlation
+ * (detector.py:222-224, reference features as kernels) and heads (:159-184), selector towers
+ * (selector.py:27-77) and 1x1 convs (:79-111), refiner feature/volume nets (refiner.py:24-52,
+ * 88-134).  w: packed [K, Cout]; bias may be NULL.  ws: split-K workspace of
+ * g6d_conv_workspace_bytes(desc) bytes (may be NULL when that returns 0). */
+int g6d_conv(const g6d_conv_desc* desc, const float* x, const float* w, const float* bias,
+             const float* pro_scale, const float* pro_shift, float* y, void* ws, g6d_stream_t stream);
+long long g6d_conv_workspace_bytes(const g6d_conv_desc* desc);
+/* [Cout, Cin, kd, kh, kw] (reference layout) -> [taps*Cin_pad, ldw] with ldw = Cout rounded up
+ * to 4; channels [Cin, Cin_pad) and columns [Cout, ldw) are zero; optional per-Cout scale
+ * (eval-mode BatchNorm fold). */
+int g6d_pack_conv_weight(const float* w, float* out, int Cout, int Cin, int Cin_pad, int taps,
+                         const float* cout_scale, g6d_stream_t stream);
+/* [rows, K] row-major -> [K, rows] (detector reference features [rfn,k,k,512] -> correlation kernels) */
+int g6d_transpose2d(const float* in, float* out, int rows, int cols, g6d_stream_t stream);
+/* y[m, n] = act(sum_k x[m,k] w[n,k] + b[n]) for small m (<= 8): weight-bandwidth bound
+ * (refiner regressor fc 32768->512, refiner.py:156-159).  w is [N, K] row-major. */
+int g6d_linear_smallm(const float* x, const float* w, const float* bias, float* y, int M, int N, int K, int act,
+                      g6d_stream_t stream);
+
+/* ------------------------------------------------------------------ detector ---------------- */
+#define G6D_DET_MAX_SCALES 8
+typedef struct g6d_det_maps {
+    int n_scales;
+    int rfn, hs, ws;                 /* output resolution (h/8, w/8) */
+    const float* map[G6D_DET_MAX_SCALES][3]; /* raw correlation [qn, Hl, Wl, rfn], level l = 0,1,2 */
+    int H[G6D_DET_MAX_SCALES][3];
+    int W[G6D_DET_MAX_SCALES][3];
+    float mu[3], inv_sigma[3], clip; /* vgg_score_stats / vgg_score_max */
+} g6d_det_maps;
+/* Fuses detector.py:225-226 (nearest x2/x4), :207-216 (normalise + clip), :243 (bilinear resize
+ * to (hs,ws)), :245 (stack), :246 score_conv (1x1x1 Conv3d 3S->64, ReLU, 64->64) and :247 (max
+ * over references).  w1 [64, 3S] (channel = scale*3 + level), w2 [64, 64].  out [qn, hs, ws, 64]. */
+int g6d_det_score_fuse(const g6d_det_maps* host_maps, int qn, const float* w1, const float* b1,
+                       const float* w2, const float* b2, float* out, g6d_stream_t stream);
+/* detector.py:85-121: first-max flat argmax of scores [qn,hs,ws,1], then
+ * position = ((x,y) + offset[y,x] + 0.5)*pool - 0.5, scale = 2**scale[y,x].
+ * out [qn, 4] = (x, y, scale, score); out_idx [qn] (int64 flat index y*ws + x). */
+int g6d_det_parse(const float* scores, const float* scales, const float* offsets, int qn, int hs, int ws,
+                  int pool_ratio, float* out, long long* out_idx, g6d_stream_t stream);
+
+/* ------------------------------------------------------------------ selector ---------------- */
+/* Load-time sums over the reference stack ref [S, P, C]: sum_s ref and sum_s ref^2, as doubles
+ * [P, C] each.  They give the first InstanceNorm3d's statistics of the correlation volume in
+ * closed form at query time (SURVEY.md 8a S2 note). */
+int g6d_sel_ref_sums(const float* ref, int S, int P, int C, double* sum1, double* sum2, g6d_stream_t stream);
+/* From q [P, C] and the sums: scale[p,c] = q[p,c]*rstd_c, shift[c] = -mean_c*rstd_c, the
+ * G6D_PRO_CORR prologue operands of the first tower conv (selector.py:28,49,63 InstanceNorm3d
+ * over (S,h,w) of que*ref). */
+int g6d_sel_corr_prologue(const float* q, const double* sum1, const double* sum2, int S, int P, int C, float eps,
+                          float* scale, float* shift, g6d_stream_t stream);
+/* The rotated-similarity score, selector.py:183-186,192-194: s[p] = sum_c q[p,c]*ref[s,p,c];
+ * score[s] = sum_p s[p]^2 / max_p s[p].  ref [S, P, C] is streamed once from HBM. */
+int g6d_sel_corr_score(const float* ref, const float* q, int S, int P, int C, float* score, g6d_stream_t stream);
+/* vp_norm (InstanceNorm2d(3), selector.py:78,201): normalise each of the L score rows [L, n]
+ * (biased var, eps) and scatter into feats[n, cstride] at channel coff + l. */
+int g6d_sel_vp_norm(const float* score, int L, int n, float eps, float* feats, int cstride, int coff,
+                    g6d_stream_t stream);
+/* selector.py:203-204: out[r,c] = max_a x[r,a,c] + embed[r,c] */
+int g6d_sel_max_angle_add(const float* x, const float* embed, float* out, int rfn, int an, int C, g6d_stream_t stream);
+/* attention.py:4-17 with the reference's channel->(d, head) mapping c = d*heads + head:
+ * q,k,v [n, C] -> out [n, C]; softmax(q_h^T k_h / sqrt(C/heads)) over keys. n <= 1024. */
+int g6d_attention(const float* q, const float* k, const float* v, float* out, int n, int C, int heads,
+                  g6d_stream_t stream);
+/* nn.LayerNorm(C) over the channel axis of each row (attention.py:19-26) */
+int g6d_layernorm(const float* x, const float* gamma, const float* beta, float* out, int rows, int C, float eps,
+                  g6d_stream_t stream);
+/* selector.py:172-175: idx = first argmax of logits [qn, rfn]; out [qn,2] = (angle[idx], logit[idx]) */
+int g6d_sel_parse(const float* logits, const float* angles, int qn, int rfn, long long* out_idx, float* out,
+                  g6d_stream_t stream);
+
+/* ------------------------------------------------------------------ refiner ----------------- */
+/* refiner.py:183-247 + operator.py:4-17: for every voxel of the sn^3 unit-cube grid rotated by
+ * the input pose (row vector @ R_in, R_in = que_poses[:, :3, :3]), project into each of the R
+ * reference views and the query view (P = K @ pose), bilinear-sample (zeros padding,
+ * align_corners=False) the C-channel feature maps, and write mean / unbiased std over the
+ * references and the query sample.
+ *   ref_feats [Q, R, fh, fw, C], que_feats [Q, fh, fw, C]
+ *   ref_Ks [Q, R, 3, 3], ref_poses [Q, R, 3, 4], que_Ks [Q, 3, 3], que_poses [Q, 3, 4]
+ *   mean_in [Q, sn^3, 2C]: channels [0,C) mean, [C,2C) query sample;  stdv [Q, sn^3, C]
+ * img_h/img_w: the image size the projections refer to (128), NOT the feature size. */
+int g6d_ref_volume_fill(const float* ref_feats, const float* que_feats, const float* ref_Ks,
+                        const float* ref_poses, const float* que_Ks, const float* que_poses, int Q, int R,
+                        int fh, int fw, int C, int sn, int img_h, int img_w, float* mean_in, float* stdv,
+                        g6d_stream_t stream);
+/* refiner.py:161-166 tail: r = normalize(x Wr^T + br) (4), t (2), s (1) from x [M,512];
+ * w [7, K] rows = fcr(4), fct(2), fcs(1).  out [M, 7] = (qw,qx,qy,qz, tx,ty, log2 scale). */
+int g6d_ref_pose_heads(const float* x, const float* w, const float* b, float* out, int M, int K, g6d_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GEN6D_B200_H */
