@@ -299,8 +299,7 @@ extern "C" int g6d_resize_nearest(const float* in, float* out, int N, int Hi, in
 }
 
 extern "C" int g6d_maxpool2x2(const float* in, float* out, int N, int H, int W, int C, g6d_stream_t stream) {
-    G6D_REQUIRE(in && out && N > 0 && H >= 2 && W >= 2 && (H & 1) == 0 && (W & 1) == 0 && (C & 3) == 0,
-                "g6d_maxpool2x2: need even H, W and C%%4==0");
+    G6D_REQUIRE(in && out && N > 0 && H >= 2 && W >= 2 && (C & 3) == 0, "g6d_maxpool2x2: need H, W >= 2 and C%%4==0");
     const long long total = (long long)N * (H / 2) * (W / 2) * (C / 4);
     maxpool2x2_kernel<<<ceil_div(total, 256), 256, 0, as_stream(stream)>>>(
         reinterpret_cast<const float4*>(in), reinterpret_cast<float4*>(out), N, H, W, C / 4);

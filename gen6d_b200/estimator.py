@@ -1,0 +1,100 @@
+"""Gen6DEstimator on the B200 networks: same constructor / build / predict contract as the
+reference's estimator.py:94-216 (numpy images and poses in, numpy pose out; `ref_info`, `cfg`).
+
+The stage sequencing is inherently serial per frame (crop depends on the detection, refinement
+k+1 on pose k), so this class keeps the reference's structure; throughput comes from the kernels,
+from keeping every reference-side tensor resident on the device, and from running independent
+frames on independent GPUs (see gen6d_b200/dist.py).
+"""
+import numpy as np
+import torch
+import yaml
+
+from . import geometry as G
+from .network import name2network
+
+
+class Gen6DEstimator:
+    default_cfg = {
+        'ref_resolution': 128,
+        'ref_view_num': 64,
+        'det_ref_view_num': 32,
+        'selector': None,
+        'detector': None,
+        'refiner': None,
+        'refine_iter': 3,
+    }
+
+    def __init__(self, cfg, modules=None):
+        """cfg: the reference's estimator yaml as a dict (configs/gen6d_pretrain.yaml).  `modules`
+        optionally injects already-built networks {'detector','selector','refiner'} (used with
+        synthetic checkpoints); otherwise they are loaded like estimator.py:117-125 does."""
+        self.cfg = {**self.default_cfg, **cfg}
+        self.ref_info = {}
+        if modules is not None:
+            self.detector, self.selector = modules['detector'], modules['selector']
+            self.refiner = modules.get('refiner')
+        else:
+            self.detector = self._load_module(self.cfg['detector'])
+            self.selector = self._load_module(self.cfg['selector'])
+            self.refiner = self._load_module(self.cfg['refiner']) if self.cfg['refiner'] is not None else None
+
+    @staticmethod
+    def _load_module(cfg_path):
+        with open(cfg_path, 'r') as f:
+            cfg = yaml.load(f, Loader=yaml.FullLoader)
+        net = name2network[cfg['network']](cfg)
+        state = torch.load(f'data/model/{cfg["name"]}/model_best.pth', map_location='cpu')
+        net.load_state_dict(state['network_state_dict'])
+        print(f'load from {cfg["name"]}/model_best.pth step {state["step"]}')
+        return net.cuda().eval()
+
+    def build(self, database, split_type='all'):
+        """estimator.py:139-171: pick 64 well-spread reference views, normalise them to 128x128
+        look-at crops, make the 5 in-plane rotated copies, and load the three networks."""
+        if split_type != 'all':
+            raise NotImplementedError("only the 'all' split (reference ids = all database ids) is supported")
+        center, vert = database.object_center(), database.object_vert()
+        ids_all = database.get_img_ids()
+        ref_ids = G.select_views_fps(database, ids_all, self.cfg['ref_view_num'])
+        res = self.cfg['ref_resolution']
+        ref_imgs, ref_Ks, ref_poses, ref_Hs = G.normalize_reference_views(database, ref_ids, res, 0.05)
+        rots = []
+        import cv2
+        for ang in (-np.pi / 2, -np.pi / 4, 0, np.pi / 4, np.pi / 2):
+            M = G.similarity_2d((res / 2, res / 2), 1.0, ang, (res / 2, res / 2)).astype(np.float32)
+            rots.append(np.stack([cv2.warpPerspective(database.get_image(i), M @ ref_Hs[k], (res, res),
+                                                      flags=cv2.INTER_LINEAR) for k, i in enumerate(ref_ids)], 0))
+        ref_imgs_rots = np.stack(rots, 0)  # an,rfn,h,w,3
+        self.detector.load_ref_imgs(ref_imgs[:self.cfg['det_ref_view_num']])
+        self.selector.load_ref_imgs(ref_imgs_rots, ref_poses, center, vert)
+        self.ref_info = {'imgs': ref_imgs, 'ref_imgs': ref_imgs_rots, 'Ks': ref_Ks, 'poses': ref_poses,
+                         'center': center, 'ref_ids': ref_ids}
+        if self.refiner is not None:
+            self.refiner.load_ref_imgs(database, ids_all)
+
+    def predict(self, que_img, que_K, pose_init=None):
+        """estimator.py:173-216.  que_img uint8 [h,w,3], que_K [3,3] -> (pose [3,4], inter_results)."""
+        inter = {}
+        if pose_init is None:
+            det = self.detector.detect_que_imgs(que_img[None])
+            position, scale_r2q = det['positions'][0], det['scales'][0]
+            crop, _ = G.crop_similarity(que_img, position, 1 / scale_r2q, 0, self.cfg['ref_resolution'])
+            inter.update(det_position=position, det_scale_r2q=scale_r2q, det_que_img=crop)
+            sel = self.selector.select_que_imgs(crop[None])
+            ref_idx, angle_r2q, scores = sel['ref_idx'][0], sel['angles'][0], sel['scores'][0]
+            inter.update(sel_angle_r2q=angle_r2q, sel_scores=scores, sel_ref_idx=ref_idx)
+            pose = G.pose_from_similarity(position, scale_r2q, angle_r2q, self.ref_info['poses'][ref_idx],
+                                          self.ref_info['Ks'][ref_idx], que_K, self.ref_info['center'])
+        else:
+            pose = pose_init
+        if self.refiner is not None:
+            poses = [pose]
+            for _ in range(self.cfg['refine_iter']):
+                pose = self.refiner.refine_que_imgs(que_img, que_K, pose, size=128, ref_num=6, ref_even=True)
+                poses.append(pose)
+            inter['refine_poses'] = poses
+        return pose, inter
+
+
+name2estimator = {'gen6d': Gen6DEstimator}

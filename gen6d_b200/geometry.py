@@ -1,0 +1,301 @@
+"""Host-side geometry of the Gen6D estimator (numpy + OpenCV), restated for this package.
+
+These are the small closed-form steps that sit between the three networks: look-at crops,
+in-plane alignment of reference views, farthest-point view selection, similarity -> rigid pose
+conversion.  Everything is float64 internally and cast to float32 at the same points the
+reference does.  Reference call sites: utils/base_utils.py:256-266,502-524,558-666,
+utils/pose_utils.py:12-111,217-244, utils/database_utils.py:8-139, dataset/database.py:400-410,
+667-694, network/refiner.py:275-341.
+
+2-D similarity / affine transforms are 3x3 homogeneous matrices here (the reference composes
+2x3 blocks); poses are [R|t] 3x4 world->camera.
+"""
+import cv2
+import numpy as np
+
+
+# ------------------------------------------------------------------------------------------ poses
+def pose_inverse(pose):
+    Rt = pose[:, :3].T
+    return np.concatenate([Rt, -Rt @ pose[:, 3:]], 1)
+
+
+def pose_compose(first, second):
+    """Apply `first`, then `second` (base_utils.py:512-521)."""
+    return np.concatenate([second[:, :3] @ first[:, :3], second[:, :3] @ first[:, 3:] + second[:, 3:]], 1)
+
+
+def pose_apply(pose, pts):
+    return pts @ pose[:, :3].T + pose[:, 3]
+
+
+def camera_center(pose):
+    return -pose[:, :3].T @ pose[:, 3]
+
+
+def project(pts, pose, K):
+    """World points -> pixels, depths (base_utils.py:256-266).  Depths with 0 < |d| < 1e-4 are
+    clamped to 1e-4, as the reference does."""
+    p = (pts @ pose[:, :3].T + pose[:, 3]) @ K.T
+    d = p[:, 2].copy()
+    tiny = (np.abs(d) < 1e-4) & (np.abs(d) > 0)
+    d[tiny] = 1e-4
+    return p[:, :2] / d[:, None], d
+
+
+def quat_to_matrix(q):
+    """(w, x, y, z) -> 3x3, the transforms3d.quaternions.quat2mat convention (pose_utils.py:239)."""
+    w, x, y, z = [float(v) for v in q]
+    n = w * w + x * x + y * y + z * z
+    if n < np.finfo(np.float64).eps:
+        return np.eye(3)
+    s = 2.0 / n
+    return np.array([[1 - s * (y * y + z * z), s * (x * y - w * z), s * (x * z + w * y)],
+                     [s * (x * y + w * z), 1 - s * (x * x + z * z), s * (y * z - w * x)],
+                     [s * (x * z - w * y), s * (y * z + w * x), 1 - s * (x * x + y * y)]])
+
+
+def rot_z(a):
+    c, s = np.cos(a), np.sin(a)
+    return np.array([[c, -s, 0.0], [s, c, 0.0], [0.0, 0.0, 1.0]])
+
+
+def look_at_rotation(xy):
+    """Rotation taking the ray through normalised image point (x, y, 1) onto the optical axis:
+    first about y by -atan(x), then about x by +atan(y) (base_utils.py:657-666)."""
+    x, y = float(xy[0]), float(xy[1])
+    a, b = -np.arctan2(x, 1.0), np.arctan2(y, 1.0)
+    ry = np.array([[np.cos(a), 0, np.sin(a)], [0, 1, 0], [-np.sin(a), 0, np.cos(a)]])
+    rx = np.array([[1, 0, 0], [0, np.cos(b), -np.sin(b)], [0, np.sin(b), np.cos(b)]])
+    return rx @ ry
+
+
+def look_at_pixel(center_px, K):
+    """(R, f): rotation that centres pixel `center_px`, and the focal length along that ray
+    (pose_utils.py:52-58 let_me_look_at_2d)."""
+    f = (K[0, 0] + K[1, 1]) / 2
+    c = np.asarray(center_px, np.float64) - K[:2, 2]
+    return look_at_rotation(c / f), np.sqrt(c @ c + f * f)
+
+
+def look_at_point(pose, K, point):
+    px, _ = project(np.asarray(point, np.float64)[None], pose, K)
+    return look_at_pixel(px[0], K)
+
+
+def inplane_angle_between(ref_pose, ref_K, que_pose, que_K, center):
+    """In-plane rotation (about the optical axis) that takes the look-at-rectified reference
+    view to the look-at-rectified query view: first angle of the static z-y-x Euler split of
+    R_que R_ref^T (pose_utils.py:60-102; only the angle output is used on the path)."""
+    Rr = look_at_point(ref_pose, ref_K, center)[0] @ ref_pose[:, :3]
+    Rq = look_at_point(que_pose, que_K, center)[0] @ que_pose[:, :3]
+    rel = Rq @ Rr.T
+    # R = Rx(c) Ry(b) Rz(a)  =>  first row = [cos b cos a, -cos b sin a, sin b]
+    return float(np.arctan2(-rel[0, 1], rel[0, 0]))
+
+
+# ------------------------------------------------------------------------------------------ warps
+def look_at_crop(img, K, pose, position, angle, scale, h, w):
+    """Rotate the camera to look at pixel `position`, spin by `angle`, zoom by `scale`, and cut
+    an (h, w) window (database_utils.py:8-25).  Returns img, K_new, pose_new, pose_rect, H."""
+    R, f = look_at_pixel(position, K)
+    R = rot_z(angle).astype(np.float32) @ R           # reference builds R_z in float32
+    f = f * scale
+    K_new = np.array([[f, 0, w / 2], [0, f, h / 2], [0, 0, 1]], np.float32)
+    H = K_new @ R @ np.linalg.inv(K)
+    out = cv2.warpPerspective(img, H, (w, h), flags=cv2.INTER_LINEAR) if img is not None else None
+    rect = np.concatenate([R, np.zeros((3, 1))], 1).astype(np.float32)
+    return out, K_new, pose_compose(pose, rect), rect, H
+
+
+def similarity_2d(position, scale, angle, target):
+    """3x3 matrix: translate `position` to the origin, scale, rotate, translate to `target`."""
+    c, s = np.cos(angle), np.sin(angle)
+    A = scale * np.array([[c, -s], [s, c]])
+    M = np.eye(3)
+    M[:2, :2] = A
+    M[:2, 2] = np.asarray(target, np.float64) - A @ np.asarray(position, np.float64)
+    return M
+
+
+def crop_similarity(img, position, scale, angle, size):
+    """base_utils.py:646-655 transformation_crop (float32 2x3 matrix, cv2.warpAffine)."""
+    # the reference accumulates the 2x3 blocks in float32; keep the same rounding
+    M = np.asarray([[1, 0, -position[0]], [0, 1, -position[1]]], np.float32)
+    S = np.asarray([[scale, 0, 0], [0, scale, 0]], np.float32)
+    Rm = np.asarray([[np.cos(angle), -np.sin(angle), 0], [np.sin(angle), np.cos(angle), 0]], np.float32)
+    T = np.asarray([[1, 0, size / 2], [0, 1, size / 2]], np.float32)
+    for nxt in (S, Rm, T):
+        M = np.concatenate([nxt[:, :2] @ M[:, :2], (nxt[:, :2] @ M[:, 2] + nxt[:, 2])[:, None]], 1)
+    return cv2.warpAffine(img, M, (size, size), flags=cv2.INTER_LINEAR), M
+
+
+# ------------------------------------------------------------------------------------------ view selection
+def farthest_point_indices(points, count):
+    """Farthest-point sampling seeded at the centroid (the centroid itself is not returned):
+    base_utils.py:558-586 with init_center=True, index_model=True -> count-1 indices."""
+    points = np.asarray(points)
+    count = min(points.shape[0], count)
+    cur = points.mean(0)
+    dist = np.full(points.shape[0], 1e8)
+    picked = []
+    for _ in range(min(count - 1, points.shape[0] - 1)):
+        dist = np.minimum(dist, np.linalg.norm(cur[None] - points, 2, 1))
+        i = int(np.argmax(dist))
+        picked.append(i)
+        cur = points[i]
+    return np.asarray(picked, dtype=np.int64)
+
+
+def select_views_fps(database, ids, count):
+    """database_utils.py:112-123 (random_fps=False): FPS over camera centres relative to the object."""
+    center = database.object_center()
+    cams = np.asarray([camera_center(database.get_pose(i)) - center for i in ids])
+    return np.asarray(ids)[farthest_point_indices(cams, count + 1)]
+
+
+def select_views_near_pose(database, center, ids, pose, count=6, even=False, even_count=128):
+    """database_utils.py:125-139: optionally re-spread with FPS, then the `count` views whose
+    viewing direction is closest (largest cosine) to that of `pose`."""
+    ids = np.asarray(ids)
+    poses = np.asarray([database.get_pose(i) for i in ids])
+    if even:
+        keep = farthest_point_indices(np.asarray([camera_center(p) for p in poses]), even_count + 1)
+        ids, poses = ids[keep], poses[keep]
+    unit = lambda v: v / np.linalg.norm(v, 2, -1, keepdims=True)
+    dirs = unit(np.asarray([camera_center(p) for p in poses]) - center[None])
+    q = unit(camera_center(pose) - center)
+    return ids[np.argsort(-(dirs @ q))[:count]]
+
+
+def normalize_reference_views(database, ids, size, margin, align_pose=None, align_K=None):
+    """database_utils.py:54-110 (rectify_rot=True, no extra rotations): every reference view is
+    re-rendered as a look-at crop of the object at a common apparent size, with the in-plane
+    orientation either 'object-up' (build time) or aligned to a given pose (refinement).
+    Returns imgs [n,size,size,3] u8, Ks, poses, Hs (masks are not used on the inference path)."""
+    center = database.object_center().astype(np.float64)
+    diameter = database.object_diameter()
+    imgs, Ks, poses, Hs = [], [], [], []
+    for i in ids:
+        pose, K = database.get_pose(i), database.get_K(i)
+        cen_px = project(center[None], pose, K)[0][0]
+        dist = np.linalg.norm(camera_center(pose) - center)
+        f_look = look_at_point(pose, K, center)[1]
+        scale = size * (1 - margin) / diameter * dist / f_look
+        if align_pose is not None:
+            angle = inplane_angle_between(pose, K, align_pose, align_K, center)
+        else:
+            v = (pose[:, :3] @ database.object_vert())[:2].astype(np.float64)
+            if np.linalg.norm(v) < 1e-5:
+                v = v + 1e-5 * np.sign(v)
+            angle = -np.arctan2(v[1], v[0]) - np.pi / 2
+        img, K_new, pose_new, _, H = look_at_crop(database.get_image(i), K, pose, cen_px, angle, scale, size, size)
+        imgs.append(img)
+        Ks.append(K_new)
+        poses.append(pose_new)
+        Hs.append(H)
+    return np.stack(imgs, 0), np.stack(Ks, 0), np.stack(poses, 0), np.stack(Hs, 0)
+
+
+# ------------------------------------------------------------------------------------------ pose from detection + selection
+def pose_from_similarity(position, scale_r2q, angle_r2q, ref_pose, ref_K, que_K, center):
+    """estimate_pose_from_similarity_transform_compose (pose_utils.py:104-111 -> :12-46): the 2-D
+    similarity (detected position / scale, selected in-plane angle) that maps the reference crop
+    into the query image fixes the object's bearing, depth and in-plane rotation."""
+    center = np.asarray(center, np.float64)
+    ref_cen = project(center[None], ref_pose, ref_K)[0][0]
+    # query -> reference similarity, then inverted (reference -> query)
+    M_q2r = similarity_2d(position, 1.0 / scale_r2q, -angle_r2q, ref_cen)
+    M_r2q = np.linalg.inv(M_q2r)
+    que_cen = M_r2q[:2, :2] @ ref_cen + M_r2q[:2, 2]
+    bearing = np.linalg.inv(que_K) @ np.array([que_cen[0], que_cen[1], 1.0])
+    bearing_xy = bearing[:2] / bearing[2]
+    scale = np.sqrt(np.linalg.det(M_r2q[:2, :2]))
+    rotation = np.arctan2(M_r2q[1, 0], M_r2q[0, 0])
+    que_f, ref_f = (que_K[0, 0] + que_K[1, 1]) / 2, (ref_K[0, 0] + ref_K[1, 1]) / 2
+    que_f_ray = np.sqrt(que_f ** 2 + np.linalg.norm(bearing_xy * que_f) ** 2)
+    ref_dist = np.linalg.norm(camera_center(ref_pose) - center)
+    que_dist = ref_dist * que_f_ray / ref_f / scale
+    ray = np.array([bearing_xy[0], bearing_xy[1], 1.0])
+    cen3d = ray / np.linalg.norm(ray) * que_dist
+    R = look_at_rotation(bearing_xy).T @ (rot_z(rotation) @ ref_pose[:, :3])
+    return np.concatenate([R, (cen3d - R @ center)[:, None]], 1)
+
+
+# ------------------------------------------------------------------------------------------ refinement bookkeeping
+class NormalizedView:
+    """The database seen through 'object in the unit sphere at the origin' coordinates
+    (dataset/database.py:667-694 NormalizedDatabase; normalize_pose :400-404)."""
+
+    def __init__(self, database):
+        self.db = database
+        self.scale = 2.0 / database.object_diameter()
+        self.offset = -self.scale * database.object_center()
+
+    def normalize_pose(self, pose):
+        R, t = pose[:3, :3], pose[:3, 3]
+        return np.concatenate([R, (R @ -self.offset + self.scale * t)[:, None]], -1).astype(np.float32)
+
+    def denormalize_pose(self, pose):
+        R, t = pose[:3, :3], pose[:3, 3]
+        return np.concatenate([R, (R @ self.offset / self.scale + t / self.scale)[:, None]], -1).astype(np.float32)
+
+    def get_pose(self, i):
+        return self.normalize_pose(self.db.get_pose(i))
+
+    def get_K(self, i):
+        return self.db.get_K(i)
+
+    def get_image(self, i):
+        return self.db.get_image(i)
+
+    def object_center(self):
+        return np.zeros(3, np.float32)
+
+    def object_diameter(self):
+        return 2.0
+
+    def object_vert(self):
+        return self.db.object_vert()
+
+
+def refine_problem(database, ref_ids, que_img, que_K, in_pose, size=128, ref_num=6, ref_even=False, margin=0.05):
+    """Everything refiner.py:285-325 prepares on the host for one refinement step: the query
+    look-at crop at the input pose and the `ref_num` nearest reference views re-rendered with
+    their in-plane orientation aligned to it."""
+    view = NormalizedView(database)
+    pose_n = view.normalize_pose(in_pose)
+    center = view.object_center()
+    f_look = look_at_point(pose_n, que_K, center)[1]
+    dist = np.linalg.norm(camera_center(pose_n) - center)
+    scale = size * (1 - margin) / view.object_diameter() * dist / f_look
+    cen_px = project(center[None].astype(np.float64), pose_n, que_K)[0][0]
+    que_crop, K_warp, pose_warp, pose_rect, _ = look_at_crop(que_img, que_K, pose_n, cen_px, 0, scale, size, size)
+    ids = select_views_near_pose(view, center, ref_ids, pose_warp, ref_num, ref_even, min(128, len(ref_ids)))
+    ref_imgs, ref_Ks, ref_poses, _ = normalize_reference_views(view, ids, size, margin, pose_warp, K_warp)
+    return {'view': view, 'que_img': que_crop, 'que_K': K_warp.astype(np.float32),
+            'que_pose': pose_warp.astype(np.float32), 'pose_rect': pose_rect, 'center': center, 'ref_ids': ids,
+            'ref_imgs': ref_imgs, 'ref_Ks': ref_Ks.astype(np.float32), 'ref_poses': ref_poses.astype(np.float32)}
+
+
+def apply_refinement(prob, quat, offset, scale):
+    """refiner.py:333-340: (scale, quaternion, 2-D offset) -> similarity transform about the object
+    centre -> rigid pose at the matching depth -> undo the look-at rectification -> undo the
+    unit-sphere normalisation (pose_utils.py:217-244)."""
+    pose_in, K, center = prob['que_pose'].astype(np.float64), prob['que_K'].astype(np.float64), prob['center']
+    cen_in = pose_apply(pose_in, center.astype(np.float64))
+    A = float(np.asarray(scale).reshape(-1)[0]) * quat_to_matrix(quat)
+    cen_que = cen_in + np.array([offset[0], offset[1], 0.0])
+    sim_t = cen_que - A @ cen_in
+    # similarity -> rigid: keep the rotation part, move the centre along its new ray to the depth
+    # implied by the scale change
+    U, S, Vt = np.linalg.svd(A)
+    Rdelta = U @ Vt
+    f = np.mean(np.diag(K)[:2])
+    depth = cen_in[2] / np.mean(np.abs(S)) * f / f
+    cen_sim = A @ cen_in + sim_t
+    cen_new = cen_sim / cen_sim[2] * depth
+    R = Rdelta @ pose_in[:3, :3]
+    pose = np.concatenate([R, (cen_new - R @ center)[:, None]], 1)
+    pose = pose_compose(pose, pose_inverse(prob['pose_rect']))
+    return prob['view'].denormalize_pose(pose)

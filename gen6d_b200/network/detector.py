@@ -138,5 +138,5 @@ class Detector(PackedModule):
             u8 = self._to_dev(que_imgs)
             o = self._detect_nhwc(ops.preprocess_u8(u8, out_c=3, imagenet_norm=False))
             out, _ = ops.det_parse(o['score_predict'], o['scale_predict'], o['offset_predict'], self.pool_ratio)
-            out = out.cpu().numpy()
+            out = self._to_host(out)
         return {'positions': out[:, :2].copy(), 'scales': out[:, 2].copy()}

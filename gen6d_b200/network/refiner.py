@@ -163,5 +163,5 @@ class VolumeRefiner(PackedModule):
             ref = ops.preprocess_u8(self._to_dev(prob['ref_imgs'][None]), out_c=4, imagenet_norm=True)
             out = self._forward_nhwc(que, self._to_dev(prob['que_K'][None]), self._to_dev(prob['que_pose'][None]), ref,
                                      self._to_dev(prob['ref_Ks'][None]), self._to_dev(prob['ref_poses'][None]))
-            out = out.cpu().numpy()[0]
+            out = self._to_host(out)[0]
         return G.apply_refinement(prob, quat=out[:4], offset=out[4:6], scale=2.0 ** out[6])

@@ -224,5 +224,5 @@ class ViewpointSelector(PackedModule):
             x = ops.preprocess_u8(self._to_dev(que_imgs), out_c=4, imagenet_norm=True)
             logits, angles, _ = self._select_nhwc(x)
             idx, out = ops.sel_parse(logits, angles)
-            idx, out, logits = idx.cpu().numpy(), out.cpu().numpy(), logits.cpu().numpy()
+            idx, out, logits = self._to_host(idx), self._to_host(out), self._to_host(logits)
         return {'ref_idx': idx, 'angles': out[:, 0].copy(), 'scores': logits}

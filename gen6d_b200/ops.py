@@ -27,8 +27,34 @@ def _p(t, dtype=torch.float32):
     return C.c_void_p(t.data_ptr())
 
 
-def _call(name, *args):
+_PROFILE = None   # when enabled: {name: [(start_event, end_event, work), ...]}
+
+
+def _call(name, *args, work=None):
+    if _PROFILE is not None and work is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        _lib.check(getattr(_lib.lib(), name)(*args), name)
+        e1.record()
+        _PROFILE.setdefault(name, []).append((e0, e1, work))
+        return
     _lib.check(getattr(_lib.lib(), name)(*args), name)
+
+
+def enable_profiling():
+    """Time every launch of the roofline kernels with CUDA events on the launching stream
+    (bench.py).  `work` is the algorithmic FLOPs (conv) or bytes (streaming kernels) of the call."""
+    global _PROFILE
+    _PROFILE = {}
+    return _PROFILE
+
+
+def collect_profile(prof):
+    global _PROFILE
+    torch.cuda.synchronize()
+    _PROFILE = None
+    return {k: {'ms': sum(a.elapsed_time(b) for a, b, _ in v), 'work': float(sum(w for _, _, w in v)), 'n': len(v)}
+            for k, v in prof.items()}
 
 
 def require_cuda():
@@ -203,7 +229,8 @@ def conv(x, pc, prologue=PRO_NONE, pro_scale=None, pro_shift=None, group_rows=1,
     if nbytes < 0:
         _lib.check(-1, 'g6d_conv_workspace_bytes')
     ws = torch.empty(nbytes // 4, device=x.device, dtype=torch.float32) if nbytes > 0 else None
-    _call('g6d_conv', C.byref(d), _p(x), _p(pc.w), _p(pc.bias), _p(pro_scale), _p(pro_shift), _p(out), _p(ws), _stream())
+    _call('g6d_conv', C.byref(d), _p(x), _p(pc.w), _p(pc.bias), _p(pro_scale), _p(pro_shift), _p(out), _p(ws), _stream(),
+          work=2.0 * B * Do * Ho * Wo * pc.cout * kd * kh * kw * pc.cin)
     return out
 
 
@@ -267,7 +294,8 @@ def sel_corr_score(ref, q, out=None):
     S, Pn, Cc = ref.shape
     if out is None:
         out = torch.empty(S, device=ref.device, dtype=torch.float32)
-    _call('g6d_sel_corr_score', _p(ref), _p(q), S, Pn, Cc, _p(out), _stream())
+    _call('g6d_sel_corr_score', _p(ref), _p(q), S, Pn, Cc, _p(out), _stream(),
+          work=4.0 * (S * Pn * Cc + Pn * Cc + S))
     return out
 
 
@@ -311,7 +339,8 @@ def ref_volume_fill(ref_feats, que_feats, ref_Ks, ref_poses, que_Ks, que_poses, 
     mean_in = torch.empty(Q, sn, sn, sn, 2 * Cc, device=ref_feats.device, dtype=torch.float32)
     stdv = torch.empty(Q, sn, sn, sn, Cc, device=ref_feats.device, dtype=torch.float32)
     _call('g6d_ref_volume_fill', _p(ref_feats), _p(que_feats), _p(ref_Ks), _p(ref_poses), _p(que_Ks), _p(que_poses),
-          Q, R, fh, fw, Cc, sn, img_h, img_w, _p(mean_in), _p(stdv), _stream())
+          Q, R, fh, fw, Cc, sn, img_h, img_w, _p(mean_in), _p(stdv), _stream(),
+          work=4.0 * Q * ((R + 1) * fh * fw * Cc + 3 * Cc * sn ** 3))
     return mean_in, stdv
 
 

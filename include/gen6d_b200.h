@@ -61,7 +61,8 @@ int g6d_resize_bilinear(const float* in, float* out, int N, int Hi, int Wi, int 
                         int out_cstride, int out_coff, g6d_stream_t stream);
 /* F.interpolate default (nearest): src = floor(dst * in / out) (network/detector.py:201) */
 int g6d_resize_nearest(const float* in, float* out, int N, int Hi, int Wi, int Ho, int Wo, int C, g6d_stream_t stream);
-/* MaxPool 2x2 stride 2 over (H, W) (VGG 'M' layers; selector MaxPool3d((1,2,2))) */
+/* MaxPool 2x2 stride 2 over (H, W), output floor(H/2) x floor(W/2) like torch (VGG M layers;
+ * selector MaxPool3d((1,2,2))) */
 int g6d_maxpool2x2(const float* in, float* out, int N, int H, int W, int C, g6d_stream_t stream);
 /* F.normalize(dim=1) == x / max(||x||_2, eps) over the channel axis of each row
  * (network/selector.py:118, network/refiner.py:69-71) */

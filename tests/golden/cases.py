@@ -95,3 +95,13 @@ def refiner_case(seed=31, qn=2, rfn=6, size=128):
             'ref_imgs': rand_images_u8(seed + 1, qn, rfn, size, size, 3),
             'que_Ks': np.repeat(K[None], qn, 0), 'que_poses': que_poses,
             'ref_Ks': np.repeat(K[None, None], qn, 0).repeat(rfn, 1), 'ref_poses': ref_poses}
+
+
+from gen6d_b200 import synthetic as _syn  # noqa: E402
+
+# Detector statistics for the estimator-level case (480x640 frame of the synthetic object, 32 refs)
+DET_STATS_EST = _syn.DET_SCORE_STATS
+
+
+def estimator_case():
+    return {'db': dict(_syn.DATABASE), 'net_cfg': {}, 'query_id': '11'}
