@@ -87,12 +87,24 @@ class ClockSampler:
 
 
 # ---------------------------------------------------------------------------------------------
+def usable_cpus():
+    """Host threads this process may really use: affinity mask capped by the cgroup CPU quota."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, 'sched_getaffinity') else (os.cpu_count() or 1)
+    try:
+        quota, period = open('/sys/fs/cgroup/cpu.max').read().split()
+        if quota != 'max':
+            n = min(n, max(1, int(float(quota) / float(period))))
+    except Exception:
+        pass
+    return max(1, n)
+
+
 def cpu_pose_fn():
     """Returns (fn, describe): fn() runs ONE network-only pose of the oracle port on the CPU."""
     from gen6d_b200 import geometry as G
     from gen6d_b200 import synthetic as syn
     from oracle import gen6d_oracle as O
-    torch.set_num_threads(os.cpu_count())
+    torch.set_num_threads(min(usable_cpus(), 64))
     sds = syn.seeded_state_dicts()
     db = syn.synthetic_database()
     g = torch.Generator().manual_seed(5)

@@ -47,6 +47,12 @@ _SIGNATURES = {
     'g6d_conv': [C.POINTER(ConvDesc), P, P, P, P, P, P, P, P],
     'g6d_conv_workspace_bytes': [C.POINTER(ConvDesc)],
     'g6d_pack_conv_weight': [P, P, I, I, I, I, P, P],
+    'g6d_conv_tc_supported': [C.POINTER(ConvDesc)],
+    'g6d_conv_tc_debug': [C.POINTER(C.c_int)],
+    'g6d_conv_tc_workspace_bytes': [C.POINTER(ConvDesc)],
+    'g6d_conv_tc': [C.POINTER(ConvDesc), P, P, P, I, P, P, P, P, P, P],
+    'g6d_pack_conv_weight_tc': [P, P, P, I, I, I, I, I, P, P],
+    'g6d_split_tf32': [P, P, P, L, P],
     'g6d_transpose2d': [P, P, I, I, P],
     'g6d_linear_smallm': [P, P, P, P, I, I, I, I, P],
     'g6d_det_score_fuse': [C.POINTER(DetMaps), I, P, P, P, P, P, P],
@@ -62,7 +68,7 @@ _SIGNATURES = {
     'g6d_ref_volume_fill': [P, P, P, P, P, P, I, I, I, I, I, I, I, I, P, P, P],
     'g6d_ref_pose_heads': [P, P, P, P, I, I, P],
 }
-_RESTYPE = {'g6d_conv_workspace_bytes': L, 'g6d_launch_count': L, 'g6d_last_error': C.c_char_p}
+_RESTYPE = {'g6d_conv_workspace_bytes': L, 'g6d_conv_tc_workspace_bytes': L, 'g6d_launch_count': L, 'g6d_last_error': C.c_char_p}
 
 _lib = None
 

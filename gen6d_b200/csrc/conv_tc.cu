@@ -1,0 +1,641 @@
+// Implicit-GEMM convolution on the 5th-generation tensor cores (tcgen05), fp32-faithful via a
+// 3xTF32 operand split:  A*B ~= A_hi*B_hi + A_hi*B_lo + A_lo*B_hi  with x_hi = tf32(x),
+// x_lo = tf32(x - x_hi); the dropped A_lo*B_lo term is O(2^-22) relative, so index selections
+// (detection cell, viewpoint) stay bit-exact against the fp32 reference while the contraction
+// runs on the tensor pipe instead of the FFMA pipe.
+//
+// GEMM view (same as conv_ffma.cu): M = B*Do*Ho*Wo, N = Cout, K = taps*Cin, channels-last.
+// One CTA computes a 128 x BLOCK_N output tile (UMMA M=128, cta_group::1, accumulator in TMEM).
+// Warp roles (320 threads):
+//   warps 0-7  A producers: gather the im2col rows of the K-block from global memory, apply the
+//              folded InstanceNorm(+ReLU) / selector q(.)ref prologue to in-bounds elements, split
+//              into tf32 hi/lo and write both tiles into shared memory in the canonical K-major
+//              SWIZZLE_128B layout the UMMA descriptor expects; then the epilogue (TMEM -> regs
+//              -> bias/activation -> global).
+//   warp 8     B producer: one elected lane issues TMA (cp.async.bulk.tensor.2d) loads of the
+//              pre-split weight tiles W_hi / W_lo [Cout, K] (K-major, 128B swizzle) signalling an
+//              mbarrier with complete_tx.
+//   warp 9     MMA issuer: one elected lane waits on the full barriers and issues 12
+//              tcgen05.mma.kind::tf32 per K-block (4 K-steps x 3 split terms); tcgen05.commit
+//              releases the stage back to the producers; the last commit signals the epilogue.
+//              This warp also owns the TMEM allocation.
+// Small-M / huge-K problems are split along K over blockIdx.z into a workspace (same
+// deterministic reduce kernel as the FFMA path).
+#include <cuda.h>
+
+#include "common.cuh"
+
+namespace g6d {
+
+constexpr int TC_BM = 128;       // rows per tile (UMMA M)
+constexpr int TC_BK = 32;        // fp32 elements per K-block = one 128-byte swizzle row
+constexpr int TC_PRODUCER_WARPS = 8;
+constexpr int TC_MAX_KB_PER_SPLIT = 64;
+constexpr int TC_THREADS = (TC_PRODUCER_WARPS + 2) * 32;
+
+struct ConvTcP {
+    const float* x; const float* bias; const float* ps; const float* pb;
+    float* y; float* ws;
+    int B, D, H, W, Cin, ics, ico, Cout, kd, kh, kw, stride, pd, ph, pw, Do, Ho, Wo, ocs, oco, pro, act;
+    long long group_rows;
+    int M, K, kblocks, splits, kb_per_split;
+};
+
+// ------------------------------------------------------------------------------------------ PTX
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.b32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    return ok != 0;
+}
+// Bounded wait: a protocol bug must never hang the GPU.  On timeout (~0.25 s) the waiter records
+// who was waiting on what in g_tc_timeout (read back with g6d_conv_tc_debug) and every wait in the
+// grid falls through, so the kernel terminates (with garbage output) instead of spinning.
+__device__ int g_tc_timeout[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int who = 0, int iter = 0) {
+    if (mbar_try_wait(bar, parity)) return;
+    const long long t0 = clock64();
+    while (!mbar_try_wait(bar, parity)) {
+        if (*(volatile int*)&g_tc_timeout[0] != 0) return;
+        if (clock64() - t0 > 500000000ll) {
+            if (atomicCAS(&g_tc_timeout[0], 0, 1) == 0) {
+                g_tc_timeout[1] = who; g_tc_timeout[2] = iter; g_tc_timeout[3] = (int)parity;
+                g_tc_timeout[4] = (int)blockIdx.x; g_tc_timeout[5] = (int)blockIdx.y; g_tc_timeout[6] = (int)blockIdx.z;
+                g_tc_timeout[7] = (int)threadIdx.x;
+            }
+            return;
+        }
+    }
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1) : "memory");
+}
+
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start
+// address >> 4 in bits [0,14); LBO (ignored for swizzled K-major) = 1 in [16,30); SBO = 1024 B
+// (8 rows x 128 B) >> 4 in [32,46); descriptor version 1 in [46,48); layout SWIZZLE_128B (=2)
+// in [61,64).  The tile base must be 1024-byte aligned (base_offset = 0).
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)(1024 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+
+// cute::UMMA::InstrDescriptor for kind::tf32, fp32 accumulate, both operands K-major:
+// c_format F32 (1) at [4,6); a_format/b_format TF32 (2) at [7,10)/[10,13); n_dim = N>>3 at
+// [17,23); m_dim = M>>4 at [24,29).
+__device__ __forceinline__ uint32_t umma_idesc_tf32(int M, int N) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                          uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+
+__device__ __forceinline__ float to_tf32(float v) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
+    return __uint_as_float(r);
+}
+
+__device__ __forceinline__ float tc_act(float v, int act) {
+    if (act == G6D_ACT_RELU) return fmaxf(v, 0.f);
+    if (act == G6D_ACT_LEAKY01) return v > 0.f ? v : 0.1f * v;
+    return v;
+}
+
+template <int BN> struct TcCfg {
+    static constexpr int A_BYTES = TC_BM * 128;            // one A tile (hi or lo)
+    static constexpr int B_BYTES = BN * 128;               // one B tile (hi or lo)
+    static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
+    static constexpr int STAGES = (200 * 1024) / STAGE_BYTES > 6 ? 6 : (200 * 1024) / STAGE_BYTES;
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+    // TMEM accumulators: NMAIN round-robin chains for the main (hi*hi) term + one for the cross terms.
+    // Each tensor-core accumulate truncates to fp32; spreading the K-blocks over several shorter,
+    // smaller-magnitude chains (summed in fp32 round-to-nearest by the epilogue) divides the
+    // resulting bias on same-sign data by ~NMAIN at no cost.
+    static constexpr int NMAIN = BN == 32 ? 7 : 3;
+    static constexpr int TMEM_COLS = (NMAIN + 1) * BN;             // 256 / 256 / 512 columns
+};
+
+// ------------------------------------------------------------------------------------------ kernel
+template <int BN>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+conv_tc_kernel(const ConvTcP p, const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CUtensorMap map_lo) {
+    using Cfg = TcCfg<BN>;
+    constexpr int STAGES = Cfg::STAGES;
+    extern __shared__ uint8_t smem_raw[];
+    // carve: [stages x (A_hi | A_lo | B_hi | B_lo)] 1024-aligned, then barriers
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t* base_ptr = smem_raw + (base - smem_u32(smem_raw));
+    const uint32_t bar_base = base + STAGES * Cfg::STAGE_BYTES;
+    auto a_hi = [&](int s) { return base + s * Cfg::STAGE_BYTES; };
+    auto a_lo = [&](int s) { return base + s * Cfg::STAGE_BYTES + Cfg::A_BYTES; };
+    auto b_hi = [&](int s) { return base + s * Cfg::STAGE_BYTES + 2 * Cfg::A_BYTES; };
+    auto b_lo = [&](int s) { return base + s * Cfg::STAGE_BYTES + 2 * Cfg::A_BYTES + Cfg::B_BYTES; };
+    auto full_a = [&](int s) { return bar_base + 8 * s; };
+    auto full_b = [&](int s) { return bar_base + 8 * (STAGES + s); };
+    auto empty = [&](int s) { return bar_base + 8 * (2 * STAGES + s); };
+    const uint32_t tmem_full = bar_base + 8 * (3 * STAGES);
+    volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(base_ptr + STAGES * Cfg::STAGE_BYTES + 8 * (3 * STAGES + 1));
+    __shared__ int4 row_info[TC_BM];     // (b, z0, y0, x0) of each tile row; b < 0 -> row beyond M
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int m_base = blockIdx.x * TC_BM;
+    const int n_base = blockIdx.y * BN;
+    const int split = blockIdx.z;
+    const int kb_begin = split * p.kb_per_split;
+    const int kb_end = min(p.kblocks, kb_begin + p.kb_per_split);
+    const int nkb = kb_end - kb_begin;
+
+    // ---- one-time setup
+    if (threadIdx.x < TC_BM) {
+        int m = m_base + threadIdx.x;
+        int4 ri = make_int4(-1, 0, 0, 0);
+        if (m < p.M) {
+            int xo = m % p.Wo; m /= p.Wo;
+            int yo = m % p.Ho; m /= p.Ho;
+            int zo = m % p.Do; m /= p.Do;
+            ri = make_int4(m, zo * p.stride - p.pd, yo * p.stride - p.ph, xo * p.stride - p.pw);
+        }
+        row_info[threadIdx.x] = ri;
+    }
+    if (warp == TC_PRODUCER_WARPS && lane == 0) {
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(full_a(s), TC_PRODUCER_WARPS);
+            mbar_init(full_b(s), 1);
+            mbar_init(empty(s), 1);
+        }
+        mbar_init(tmem_full, 1);
+        fence_barrier_init();
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_hi) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_lo) : "memory");
+    }
+    if (warp == TC_PRODUCER_WARPS + 1) {   // TMEM allocation (warp-collective)
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+                     ::"r"(smem_u32((const void*)tmem_slot)), "n"(Cfg::TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_acc = *tmem_slot;
+
+    if (warp < TC_PRODUCER_WARPS) {
+        // =============================== A producers ===============================
+        const int chunk = threadIdx.x & 7;          // 16-byte chunk (4 floats) within the 128-byte K row
+        const int rg = threadIdx.x >> 3;            // 0..31; rows rg + 32*i
+        // Per-row constants: pointer to the tap-(0,0,0) element of this thread's chunk (may point
+        // before the tensor for padded rows; only dereferenced when the tap is in bounds), the
+        // base input coordinates, and the prologue operand rows.
+        const float* rowp[4];
+        const float* scp[4];
+        const float* shp[4];
+        int rz[4], ry[4], rx[4];
+        bool rv[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int4 ri = row_info[rg + 32 * i];
+            rv[i] = ri.x >= 0;
+            rz[i] = ri.y; ry[i] = ri.z; rx[i] = ri.w;
+            const long long b = rv[i] ? ri.x : 0;
+            const long long sp0 = ((long long)ri.y * p.H + ri.z) * p.W + ri.w;
+            rowp[i] = p.x + (b * p.D * p.H * p.W + sp0) * p.ics + p.ico + chunk * 4;
+            if (p.pro == G6D_PRO_CORR) {
+                scp[i] = p.ps + sp0 * p.Cin + chunk * 4;
+                shp[i] = p.pb + chunk * 4;
+            } else {
+                const long long g = b / p.group_rows;
+                scp[i] = p.ps + g * p.Cin + chunk * 4;
+                shp[i] = p.pb + g * p.Cin + chunk * 4;
+            }
+        }
+        // K-block cursor (tap, channel), advanced incrementally: no divisions inside the loop
+        int c0, kx, ky, kz;
+        {
+            const int k = kb_begin * TC_BK;
+            int tap = 0;
+            c0 = k;
+            if (p.K != p.Cin) { tap = k / p.Cin; c0 = k - tap * p.Cin; }
+            kx = tap % p.kw;
+            const int tq = tap / p.kw;
+            ky = tq % p.kh;
+            kz = tq / p.kh;
+        }
+        auto advance = [&]() {
+            c0 += TC_BK;
+            if (c0 == p.Cin) {
+                c0 = 0;
+                if (++kx == p.kw) { kx = 0; if (++ky == p.kh) { ky = 0; ++kz; } }
+            }
+        };
+
+        float4 cur[4], nxt[4];
+        unsigned cur_ok = 0, nxt_ok = 0;            // bit i: row i's tap is in bounds
+        int cur_c = 0, nxt_c = 0;
+        long long cur_sp = 0, nxt_sp = 0;           // spatial offset of the tap (for the CORR prologue)
+
+        auto issue_loads = [&]() {
+            const long long tap_sp = ((long long)kz * p.H + ky) * p.W + kx;
+            const long long off = tap_sp * p.ics + c0;
+            nxt_ok = 0; nxt_c = c0; nxt_sp = tap_sp;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const bool inb = rv[i] && (unsigned)(rz[i] + kz) < (unsigned)p.D && (unsigned)(ry[i] + ky) < (unsigned)p.H &&
+                                 (unsigned)(rx[i] + kx) < (unsigned)p.W;
+                nxt[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (inb) {
+                    nxt[i] = __ldg(reinterpret_cast<const float4*>(rowp[i] + off));
+                    nxt_ok |= 1u << i;
+                }
+            }
+            advance();
+        };
+
+        if (nkb > 0) issue_loads();
+        for (int it = 0; it < nkb; ++it) {
+            const int s = it % STAGES;
+            const uint32_t n_use = it / STAGES;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) cur[i] = nxt[i];
+            cur_ok = nxt_ok; cur_c = nxt_c; cur_sp = nxt_sp;
+            if (it + 1 < nkb) issue_loads();
+            // prologue on in-bounds elements (zero padding stays zero)
+            if (p.pro != G6D_PRO_NONE) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    if (cur_ok & (1u << i)) {
+                        const long long so = p.pro == G6D_PRO_CORR ? cur_sp * p.Cin + cur_c : (long long)cur_c;
+                        const float4 sc = __ldg(reinterpret_cast<const float4*>(scp[i] + so));
+                        const float4 sh = __ldg(reinterpret_cast<const float4*>(shp[i] + cur_c));
+                        float4 v = cur[i];
+                        v.x = fmaf(v.x, sc.x, sh.x); v.y = fmaf(v.y, sc.y, sh.y);
+                        v.z = fmaf(v.z, sc.z, sh.z); v.w = fmaf(v.w, sc.w, sh.w);
+                        if (p.pro == G6D_PRO_AFFINE_RELU) {
+                            v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
+                        }
+                        cur[i] = v;
+                    }
+                }
+            }
+            mbar_wait(empty(s), (n_use & 1) ^ 1, 1, it);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                // 3xTF32 split with full-rate integer ops: hi = round-to-nearest (ties away) of the
+                // fp32 mantissa to 10 bits (same as cvt.rna.tf32.f32 for finite values), lo = v - hi
+                // (exact in fp32; the tensor core ignores its low 13 mantissa bits).
+                const float4 v = cur[i];
+                float4 hi, lo;
+                hi.x = __uint_as_float((__float_as_uint(v.x) + 0x1000u) & 0xFFFFE000u);
+                hi.y = __uint_as_float((__float_as_uint(v.y) + 0x1000u) & 0xFFFFE000u);
+                hi.z = __uint_as_float((__float_as_uint(v.z) + 0x1000u) & 0xFFFFE000u);
+                hi.w = __uint_as_float((__float_as_uint(v.w) + 0x1000u) & 0xFFFFE000u);
+                lo.x = v.x - hi.x; lo.y = v.y - hi.y; lo.z = v.z - hi.z; lo.w = v.w - hi.w;
+                const int r = rg + 32 * i;
+                const uint32_t off = r * 128 + ((chunk ^ (r & 7)) << 4);     // Swizzle<3,4,3>
+                asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(a_hi(s) + off), "f"(hi.x), "f"(hi.y),
+                             "f"(hi.z), "f"(hi.w) : "memory");
+                asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(a_lo(s) + off), "f"(lo.x), "f"(lo.y),
+                             "f"(lo.z), "f"(lo.w) : "memory");
+            }
+            fence_proxy_async();          // generic-proxy smem writes -> visible to the tensor core (async proxy)
+            __syncwarp();
+            if (lane == 0) mbar_arrive(full_a(s));
+        }
+
+        // =============================== epilogue ===============================
+        mbar_wait(tmem_full, 0, 2, nkb);
+        tc_fence_after();
+        const int quad = warp & 3;                      // TMEM lane quadrant this warp may read
+        const int row = quad * 32 + lane;
+        const int m = m_base + row;
+        constexpr int HALF = BN / 2;                    // warps 0-3: columns [0,HALF), warps 4-7: [HALF,BN)
+        const int col0 = (warp >> 2) * HALF;
+        const bool partial = p.splits > 1;
+#pragma unroll
+        for (int cc = 0; cc < HALF; cc += 16) {
+            float accv[16];
+            const uint32_t taddr = tmem_acc + ((uint32_t)(quad * 32) << 16) + (uint32_t)(col0 + cc);
+            const int n_acc = nkb < Cfg::NMAIN ? nkb : Cfg::NMAIN;    // main chains that were written
+#pragma unroll
+            for (int a = 0; a <= Cfg::NMAIN; ++a) {
+                const bool used = a == Cfg::NMAIN || a < n_acc;      // last = cross-term accumulator
+                uint32_t r[16];
+                if (used) {
+                    asm volatile(
+                        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+                        : "r"(taddr + (uint32_t)(a * BN)));
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) accv[j] = a == 0 ? __uint_as_float(r[j]) : accv[j] + __uint_as_float(r[j]);
+                }
+            }
+            if (m < p.M) {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    const int n = n_base + col0 + cc + j;
+                    if (n < p.Cout) {
+                        float v = accv[j];                                           // main chains + cross terms
+                        if (partial) {
+                            p.ws[((long long)split * p.M + m) * p.Cout + n] = v;
+                        } else {
+                            if (p.bias) v += __ldg(p.bias + n);
+                            p.y[(long long)m * p.ocs + p.oco + n] = tc_act(v, p.act);
+                        }
+                    }
+                }
+            }
+        }
+        tc_fence_before();
+    } else if (warp == TC_PRODUCER_WARPS) {
+        // =============================== B producer (TMA) ===============================
+        if (lane == 0) {
+            for (int it = 0; it < nkb; ++it) {
+                const int s = it % STAGES;
+                const uint32_t n_use = it / STAGES;
+                mbar_wait(empty(s), (n_use & 1) ^ 1, 3, it);
+                mbar_expect_tx(full_b(s), 2 * Cfg::B_BYTES);
+                const int k = (kb_begin + it) * TC_BK;
+                tma_load_2d(b_hi(s), &map_hi, full_b(s), k, n_base);
+                tma_load_2d(b_lo(s), &map_lo, full_b(s), k, n_base);
+            }
+        }
+    } else {
+        // =============================== MMA issuer ===============================
+        if (lane == 0) {
+            const uint32_t idesc = umma_idesc_tf32(TC_BM, BN);
+            for (int it = 0; it < nkb; ++it) {
+                const int s = it % STAGES;
+                const uint32_t n_use = it / STAGES;
+                mbar_wait(full_a(s), n_use & 1, 4, it);
+                mbar_wait(full_b(s), n_use & 1, 5, it);
+                tc_fence_after();
+                const uint64_t dah = umma_desc_sw128(a_hi(s)), dal = umma_desc_sw128(a_lo(s));
+                const uint64_t dbh = umma_desc_sw128(b_hi(s)), dbl = umma_desc_sw128(b_lo(s));
+#pragma unroll
+                for (int ks = 0; ks < TC_BK / 8; ++ks) {
+                    const uint64_t adv = (uint64_t)((ks * 32) >> 4);   // +32 bytes of K per step, in 16-byte units
+                    // The small cross terms get their own TMEM accumulator, the main term rotates over
+                    // NMAIN accumulators (see TcCfg).
+                    const uint32_t main_acc = tmem_acc + (uint32_t)((it % Cfg::NMAIN) * BN);
+                    const uint32_t cross_acc = tmem_acc + (uint32_t)(Cfg::NMAIN * BN);
+                    umma_tf32(cross_acc, dal + adv, dbh + adv, idesc, (it > 0 || ks > 0) ? 1u : 0u);
+                    umma_tf32(cross_acc, dah + adv, dbl + adv, idesc, 1u);
+                    umma_tf32(main_acc, dah + adv, dbh + adv, idesc, (it >= Cfg::NMAIN || ks > 0) ? 1u : 0u);
+                }
+                umma_commit(empty(s));            // frees the stage once these MMAs have read it
+            }
+            umma_commit(tmem_full);               // accumulator complete -> epilogue
+        }
+    }
+    __syncthreads();
+    if (warp == TC_PRODUCER_WARPS + 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_acc), "n"(Cfg::TMEM_COLS) : "memory");
+    }
+}
+
+__global__ void conv_tc_reduce_kernel(const float* __restrict__ ws, const float* __restrict__ bias,
+                                      float* __restrict__ y, int M, int Cout, int splits, int ocs, int oco, int act) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (long long)M * Cout) return;
+    const int n = (int)(i % Cout);
+    const long long m = i / Cout;
+    float v = 0.f;
+    for (int s = 0; s < splits; ++s) v += ws[(long long)s * M * Cout + i];
+    if (bias) v += bias[n];
+    y[m * ocs + oco + n] = tc_act(v, act);
+}
+
+// ------------------------------------------------------------------------------------------ host
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void* sym = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(sym);
+    }
+    return fn;
+}
+
+// 2-D tensor map over W [rows = Cout_pad, cols = K] fp32, box = [32 cols, bn rows], 128B swizzle
+static int make_weight_map(CUtensorMap* map, const float* w, int rows, int K, int bn) {
+    EncodeTiledFn enc = get_encode_fn();
+    if (!enc) { set_error("g6d_conv_tc: cuTensorMapEncodeTiled unavailable"); return G6D_ECUDA; }
+    cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)K * sizeof(float)};
+    cuuint32_t box[2] = {(cuuint32_t)TC_BK, (cuuint32_t)bn};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(w), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("g6d_conv_tc: cuTensorMapEncodeTiled failed (%d)", (int)r); return G6D_ECUDA; }
+    return G6D_OK;
+}
+
+static int tc_block_n(int Cout) { return Cout > 64 ? 128 : (Cout > 32 ? 64 : 32); }
+
+static int fill_tc_params(const g6d_conv_desc* d, ConvTcP& p) {
+    G6D_REQUIRE(d != nullptr, "g6d_conv_tc: null desc");
+    G6D_REQUIRE(d->B > 0 && d->D > 0 && d->H > 0 && d->W > 0 && d->Cin > 0 && d->Cout > 0, "g6d_conv_tc: bad dims");
+    G6D_REQUIRE(d->kd > 0 && d->kh > 0 && d->kw > 0 && d->stride > 0, "g6d_conv_tc: bad kernel/stride");
+    G6D_REQUIRE((d->Cin % TC_BK) == 0, "g6d_conv_tc: Cin (%d) must be a multiple of %d", d->Cin, TC_BK);
+    G6D_REQUIRE((d->in_cstride & 3) == 0 && (d->in_coff & 3) == 0, "g6d_conv_tc: in_cstride/in_coff must be multiples of 4");
+    G6D_REQUIRE(d->in_coff + d->Cin <= d->in_cstride, "g6d_conv_tc: input channel slice out of row");
+    G6D_REQUIRE(d->out_coff + d->Cout <= d->out_cstride, "g6d_conv_tc: output channel slice out of row");
+    const int Do = (d->D + 2 * d->pd - d->kd) / d->stride + 1;
+    const int Ho = (d->H + 2 * d->ph - d->kh) / d->stride + 1;
+    const int Wo = (d->W + 2 * d->pw - d->kw) / d->stride + 1;
+    G6D_REQUIRE(Do == d->Do && Ho == d->Ho && Wo == d->Wo, "g6d_conv_tc: output dims mismatch");
+    G6D_REQUIRE(d->prologue >= 0 && d->prologue <= 3 && d->act >= 0 && d->act <= 2, "g6d_conv_tc: bad prologue/act");
+    const long long M = (long long)d->B * Do * Ho * Wo;
+    const long long K = (long long)d->kd * d->kh * d->kw * d->Cin;
+    G6D_REQUIRE(M < (1ll << 31) && K < (1ll << 31), "g6d_conv_tc: problem too large");
+    p.B = d->B; p.D = d->D; p.H = d->H; p.W = d->W; p.Cin = d->Cin; p.ics = d->in_cstride; p.ico = d->in_coff;
+    p.Cout = d->Cout; p.kd = d->kd; p.kh = d->kh; p.kw = d->kw; p.stride = d->stride; p.pd = d->pd; p.ph = d->ph;
+    p.pw = d->pw; p.Do = Do; p.Ho = Ho; p.Wo = Wo; p.ocs = d->out_cstride; p.oco = d->out_coff; p.pro = d->prologue;
+    p.act = d->act; p.group_rows = d->group_rows > 0 ? d->group_rows : 1;
+    p.M = (int)M; p.K = (int)K; p.kblocks = (int)(K / TC_BK);
+    const int bn = tc_block_n(d->Cout);
+    const long long ctas = (long long)ceil_div(M, TC_BM) * ceil_div(d->Cout, bn);
+    int splits = 1;
+    if (ctas < kNumSMs && p.kblocks >= 16) {
+        splits = (int)((kNumSMs + ctas - 1) / ctas);
+        splits = splits > p.kblocks / 8 ? p.kblocks / 8 : splits;
+        splits = splits < 1 ? 1 : splits;
+    }
+    // The tensor core adds each K-step into the fp32 accumulator with truncation; over very long
+    // K chains of same-sign products (detector correlation: K = 115200 of post-ReLU features)
+    // that is a systematic bias of ~4e-5 relative.  For long-K problems (K > 8192) the chain per
+    // CTA is bounded to 64 K-blocks (2048 terms) and the partials are summed in fp32 round-to-nearest.
+    const int min_splits = p.kblocks > 256 ? (p.kblocks + TC_MAX_KB_PER_SPLIT - 1) / TC_MAX_KB_PER_SPLIT : 1;
+    splits = splits < min_splits ? min_splits : splits;
+    splits = splits > 64 ? 64 : splits;
+    p.kb_per_split = (p.kblocks + splits - 1) / splits;
+    p.splits = (p.kblocks + p.kb_per_split - 1) / p.kb_per_split;
+    return G6D_OK;
+}
+
+template <int BN>
+static int launch_tc(const ConvTcP& p, const CUtensorMap& mh, const CUtensorMap& ml, cudaStream_t st) {
+    using Cfg = TcCfg<BN>;
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+        if (e != cudaSuccess) { set_error("g6d_conv_tc: cannot opt in to %d B of shared memory: %s", Cfg::SMEM_BYTES, cudaGetErrorString(e)); return G6D_ECUDA; }
+        configured = true;
+    }
+    dim3 grid(ceil_div(p.M, TC_BM), ceil_div(p.Cout, BN), p.splits);
+    conv_tc_kernel<BN><<<grid, TC_THREADS, Cfg::SMEM_BYTES, st>>>(p, mh, ml);
+    G6D_CHECK_LAUNCH("g6d_conv_tc");
+    return G6D_OK;
+}
+
+// elementwise tf32 split of an fp32 array (detector reference features used as kernels)
+__global__ void split_tf32_kernel(const float* __restrict__ in, float* __restrict__ hi, float* __restrict__ lo, long long n) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float v = in[i];
+    const float h = to_tf32(v);
+    hi[i] = h;
+    lo[i] = to_tf32(v - h);
+}
+
+// [Cout, Cin, taps] (reference layout) -> hi/lo [rows_pad, taps*Cin_pad], K index = tap*Cin_pad + c
+__global__ void pack_conv_weight_tc_kernel(const float* __restrict__ w, float* __restrict__ hi, float* __restrict__ lo,
+                                           int Cout, int Cin, int Cin_pad, int taps, int rows_pad,
+                                           const float* __restrict__ scale) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long K = (long long)taps * Cin_pad;
+    if (i >= K * rows_pad) return;
+    const int o = (int)(i / K);
+    const long long k = i % K;
+    const int tap = (int)(k / Cin_pad), c = (int)(k % Cin_pad);
+    float v = 0.f;
+    if (o < Cout && c < Cin) {
+        v = w[((long long)o * Cin + c) * taps + tap];
+        if (scale) v *= scale[o];
+    }
+    const float h = to_tf32(v);
+    hi[i] = h;
+    lo[i] = to_tf32(v - h);
+}
+
+}  // namespace g6d
+
+using namespace g6d;
+
+// Debug aid: copies the 8-int timeout record (0 = no timeout; else [1]=waiter role 1 A-producer/empty,
+// 2 epilogue/tmem_full, 3 B-producer/empty, 4 MMA/full_a, 5 MMA/full_b; [2]=iteration; [3]=parity;
+// [4..6]=block; [7]=thread) and clears it.  Synchronises the device.
+extern "C" int g6d_conv_tc_debug(int* host_out8) {
+    G6D_REQUIRE(host_out8 != nullptr, "g6d_conv_tc_debug: null");
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) { set_error("g6d_conv_tc_debug: sync: %s", cudaGetErrorString(e)); return G6D_ECUDA; }
+    e = cudaMemcpyFromSymbol(host_out8, g_tc_timeout, sizeof(int) * 8);
+    if (e != cudaSuccess) { set_error("g6d_conv_tc_debug: %s", cudaGetErrorString(e)); return G6D_ECUDA; }
+    int zeros[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    cudaMemcpyToSymbol(g_tc_timeout, zeros, sizeof(zeros));
+    return G6D_OK;
+}
+
+extern "C" int g6d_conv_tc_supported(const g6d_conv_desc* d) {
+    if (!d) return 0;
+    return (d->Cin % TC_BK) == 0 && d->Cout >= 16 && (d->in_cstride & 3) == 0 && (d->in_coff & 3) == 0 ? 1 : 0;
+}
+
+extern "C" long long g6d_conv_tc_workspace_bytes(const g6d_conv_desc* desc) {
+    ConvTcP p{};
+    if (fill_tc_params(desc, p) != G6D_OK) return -1;
+    return p.splits > 1 ? (long long)p.splits * p.M * p.Cout * (long long)sizeof(float) : 0;
+}
+
+extern "C" int g6d_conv_tc(const g6d_conv_desc* desc, const float* x, const float* w_hi, const float* w_lo,
+                           int w_rows, const float* bias, const float* pro_scale, const float* pro_shift, float* y,
+                           void* ws, g6d_stream_t stream) {
+    ConvTcP p{};
+    int rc = fill_tc_params(desc, p);
+    if (rc != G6D_OK) return rc;
+    G6D_REQUIRE(x && w_hi && w_lo && y, "g6d_conv_tc: null tensor pointer");
+    G6D_REQUIRE(w_rows >= p.Cout, "g6d_conv_tc: weight rows (%d) < Cout (%d)", w_rows, p.Cout);
+    if (p.pro != G6D_PRO_NONE) G6D_REQUIRE(pro_scale && pro_shift, "g6d_conv_tc: prologue operands missing");
+    if (p.splits > 1) G6D_REQUIRE(ws != nullptr, "g6d_conv_tc: split-K workspace required (%d splits)", p.splits);
+    p.x = x; p.bias = bias; p.ps = pro_scale; p.pb = pro_shift; p.y = y; p.ws = (float*)ws;
+    const int bn = tc_block_n(p.Cout);
+    CUtensorMap mh, ml;
+    if ((rc = make_weight_map(&mh, w_hi, w_rows, p.K, bn)) != G6D_OK) return rc;
+    if ((rc = make_weight_map(&ml, w_lo, w_rows, p.K, bn)) != G6D_OK) return rc;
+    cudaStream_t st = as_stream(stream);
+    if (bn == 128) rc = launch_tc<128>(p, mh, ml, st);
+    else if (bn == 64) rc = launch_tc<64>(p, mh, ml, st);
+    else rc = launch_tc<32>(p, mh, ml, st);
+    if (rc != G6D_OK) return rc;
+    if (p.splits > 1) {
+        const long long n = (long long)p.M * p.Cout;
+        conv_tc_reduce_kernel<<<ceil_div(n, 256), 256, 0, st>>>(p.ws, bias, y, p.M, p.Cout, p.splits, p.ocs, p.oco, p.act);
+        G6D_CHECK_LAUNCH("g6d_conv_tc(splitk reduce)");
+    }
+    return G6D_OK;
+}
+
+extern "C" int g6d_split_tf32(const float* in, float* hi, float* lo, long long n, g6d_stream_t stream) {
+    G6D_REQUIRE(in && hi && lo && n > 0, "g6d_split_tf32: bad args");
+    split_tf32_kernel<<<ceil_div(n, 256), 256, 0, as_stream(stream)>>>(in, hi, lo, n);
+    G6D_CHECK_LAUNCH("g6d_split_tf32");
+    return G6D_OK;
+}
+
+extern "C" int g6d_pack_conv_weight_tc(const float* w, float* out_hi, float* out_lo, int Cout, int Cin, int Cin_pad,
+                                       int taps, int rows_pad, const float* cout_scale, g6d_stream_t stream) {
+    G6D_REQUIRE(w && out_hi && out_lo && Cout > 0 && Cin > 0 && Cin_pad >= Cin && taps > 0 && rows_pad >= Cout,
+                "g6d_pack_conv_weight_tc: bad args");
+    const long long total = (long long)taps * Cin_pad * rows_pad;
+    pack_conv_weight_tc_kernel<<<ceil_div(total, 256), 256, 0, as_stream(stream)>>>(w, out_hi, out_lo, Cout, Cin, Cin_pad,
+                                                                                    taps, rows_pad, cout_scale);
+    G6D_CHECK_LAUNCH("g6d_pack_conv_weight_tc");
+    return G6D_OK;
+}

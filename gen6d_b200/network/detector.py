@@ -56,8 +56,11 @@ class Detector(PackedModule):
         kernels = []
         for f in feats:
             rfn, k, _, c = f.shape
-            w = ops.transpose_to_packed(f.reshape(rfn, k * k * c))
-            kernels.append(ops.PackedConv(w, None, c, rfn, (1, k, k), 1, (0, k // 2, k // 2)))
+            flat = f.reshape(rfn, k * k * c)
+            pc = ops.PackedConv(ops.transpose_to_packed(flat), None, c, rfn, (1, k, k), 1, (0, k // 2, k // 2))
+            if rfn >= 16:   # channels-last features [rfn, (ky,kx,c)] are already the K-major B operand
+                pc.w_hi, pc.w_lo = ops.split_tf32(flat)
+            kernels.append(pc)
         self.ref_kernels = kernels
 
     def scale_sizes(self, hq, wq):

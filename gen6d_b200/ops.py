@@ -5,6 +5,7 @@ checks its tensors (CUDA, contiguous, dtype), takes raw pointers and calls into
 libgen6d_b200.so on torch's current stream.  Activations are fp32 channels-last.
 """
 import ctypes as C
+import os
 from dataclasses import dataclass
 from typing import Optional
 
@@ -173,6 +174,13 @@ class PackedConv:
     k: tuple          # (kd, kh, kw)
     stride: int = 1
     pad: tuple = (0, 0, 0)
+    w_hi: Optional[torch.Tensor] = None   # tensor-core path: [rows, K] tf32 hi / lo split (K-major)
+    w_lo: Optional[torch.Tensor] = None
+
+
+def conv_path():
+    """'tc' (tcgen05 3xTF32, default) or 'ffma' (fp32 CUDA-core fallback for A/B checks): env G6D_CONV_PATH."""
+    return os.environ.get('G6D_CONV_PATH', 'tc')
 
 
 def pack_conv(weight, bias=None, stride=1, pad=None, cin_pad=None, cout_scale=None, bias_override=None):
@@ -195,7 +203,20 @@ def pack_conv(weight, bias=None, stride=1, pad=None, cin_pad=None, cout_scale=No
           _p(cout_scale.contiguous()) if cout_scale is not None else None, _stream())
     b = bias_override if bias_override is not None else bias
     b = b.detach().to(torch.float32).contiguous() if b is not None else None
-    return PackedConv(out, b, cin_pad, cout, k3, stride, pad)
+    pc = PackedConv(out, b, cin_pad, cout, k3, stride, pad)
+    if cin_pad % 32 == 0 and cout >= 16:
+        rows = (cout + 7) // 8 * 8
+        pc.w_hi = torch.empty(rows, taps * cin_pad, device=w.device, dtype=torch.float32)
+        pc.w_lo = torch.empty_like(pc.w_hi)
+        _call('g6d_pack_conv_weight_tc', _p(w), _p(pc.w_hi), _p(pc.w_lo), cout, cin, cin_pad, taps, rows,
+              _p(cout_scale.contiguous()) if cout_scale is not None else None, _stream())
+    return pc
+
+
+def split_tf32(x):
+    hi, lo = torch.empty_like(x), torch.empty_like(x)
+    _call('g6d_split_tf32', _p(x), _p(hi), _p(lo), x.numel(), _stream())
+    return hi, lo
 
 
 def transpose_to_packed(x2d):
@@ -225,6 +246,15 @@ def conv(x, pc, prologue=PRO_NONE, pro_scale=None, pro_shift=None, group_rows=1,
     d = _lib.ConvDesc(B=B, D=D, H=H, W=W, Cin=pc.cin, in_cstride=cs, in_coff=in_coff, Cout=pc.cout, kd=kd, kh=kh,
                       kw=kw, stride=s, pd=pd, ph=ph, pw=pw, Do=Do, Ho=Ho, Wo=Wo, out_cstride=out.shape[-1],
                       out_coff=out_coff, prologue=prologue, group_rows=group_rows, act=act)
+    work = 2.0 * B * Do * Ho * Wo * pc.cout * kd * kh * kw * pc.cin
+    if pc.w_hi is not None and conv_path() == 'tc' and _lib.lib().g6d_conv_tc_supported(C.byref(d)):
+        nbytes = _lib.lib().g6d_conv_tc_workspace_bytes(C.byref(d))
+        if nbytes < 0:
+            _lib.check(-1, 'g6d_conv_tc_workspace_bytes')
+        ws = torch.empty(nbytes // 4, device=x.device, dtype=torch.float32) if nbytes > 0 else None
+        _call('g6d_conv_tc', C.byref(d), _p(x), _p(pc.w_hi), _p(pc.w_lo), pc.w_hi.shape[0], _p(pc.bias), _p(pro_scale),
+              _p(pro_shift), _p(out), _p(ws), _stream(), work=work)
+        return out
     nbytes = _lib.lib().g6d_conv_workspace_bytes(C.byref(d))
     if nbytes < 0:
         _lib.check(-1, 'g6d_conv_workspace_bytes')

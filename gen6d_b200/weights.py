@@ -30,13 +30,29 @@ def seeded_tensor(seed, name, ref):
     if leaf == 'running_var':
         return torch.rand(shape, generator=g) * 0.4 + 0.8
     if leaf == 'bias':
-        return (torch.rand(shape, generator=g) - 0.5) * 0.1
+        b = (torch.rand(shape, generator=g) - 0.5) * 0.1
+        if name in _OUTPUT_BIAS:
+            b = b * 0.2 + torch.tensor(_OUTPUT_BIAS[name])
+        return b
     if leaf == 'weight' and len(shape) == 1:  # BatchNorm / LayerNorm scale
         return torch.rand(shape, generator=g) * 0.4 + 0.8
     fan_in = 1
     for s in shape[1:]:
         fan_in *= s
-    return torch.randn(shape, generator=g) * (2.0 / fan_in) ** 0.5
+    w = torch.randn(shape, generator=g) * (2.0 / fan_in) ** 0.5
+    return w * _OUTPUT_GAIN.get(name, 1.0)
+
+
+# Output heads that regress geometric quantities are given small gains so that the synthetic
+# checkpoints behave like a (weakly) trained model: the refiner predicts near-identity pose
+# updates (quaternion ~ (1,0,0,0), sub-pixel offsets, log2-scale ~ 0) and the detector predicts
+# scale factors near 1.  Without this, random heads throw every pose far off the object and the
+# refinement chain becomes an ill-conditioned (chaotic) map on featureless background crops.
+_OUTPUT_GAIN = {
+    'regressor.fcr.weight': 0.02, 'regressor.fct.weight': 0.05, 'regressor.fcs.weight': 0.02,
+    'scale_predict.4.weight': 0.03, 'offset_predict.4.weight': 0.03,
+}
+_OUTPUT_BIAS = {'regressor.fcr.bias': (1.0, 0.0, 0.0, 0.0)}
 
 
 def seeded_state_dict(module_or_spec, seed=0):

@@ -125,6 +125,24 @@ long long g6d_conv_workspace_bytes(const g6d_conv_desc* desc);
  * (eval-mode BatchNorm fold). */
 int g6d_pack_conv_weight(const float* w, float* out, int Cout, int Cin, int Cin_pad, int taps,
                          const float* cout_scale, g6d_stream_t stream);
+/* ---- tensor-core path (tcgen05, 3xTF32 split: fp32-faithful on the tensor pipe) -------------
+ * Same contract as g6d_conv, for problems with Cin % 32 == 0 and Cout >= 16
+ * (g6d_conv_tc_supported).  Weights are pre-split [w_rows >= Cout, K] K-major arrays
+ * (K = tap*Cin + c): w_hi = tf32(w), w_lo = tf32(w - w_hi), see g6d_pack_conv_weight_tc /
+ * g6d_split_tf32.  A tiles are gathered + transformed by producer warps, B tiles arrive by TMA,
+ * accumulators live in TMEM. */
+int g6d_conv_tc_supported(const g6d_conv_desc* desc);
+/* debug: host_out8[0] != 0 if a pipeline wait inside g6d_conv_tc timed out (kernel bailed out); syncs */
+int g6d_conv_tc_debug(int* host_out8);
+long long g6d_conv_tc_workspace_bytes(const g6d_conv_desc* desc);
+int g6d_conv_tc(const g6d_conv_desc* desc, const float* x, const float* w_hi, const float* w_lo, int w_rows,
+                const float* bias, const float* pro_scale, const float* pro_shift, float* y, void* ws,
+                g6d_stream_t stream);
+/* [Cout, Cin, taps] (reference layout) -> hi/lo [rows_pad, taps*Cin_pad]; optional BN-fold scale */
+int g6d_pack_conv_weight_tc(const float* w, float* out_hi, float* out_lo, int Cout, int Cin, int Cin_pad, int taps,
+                            int rows_pad, const float* cout_scale, g6d_stream_t stream);
+/* hi = tf32(x), lo = tf32(x - hi), elementwise (detector reference features as kernels) */
+int g6d_split_tf32(const float* in, float* hi, float* lo, long long n, g6d_stream_t stream);
 /* [rows, K] row-major -> [K, rows] (detector reference features [rfn,k,k,512] -> correlation kernels) */
 int g6d_transpose2d(const float* in, float* out, int rows, int cols, g6d_stream_t stream);
 /* y[m, n] = act(sum_k x[m,k] w[n,k] + b[n]) for small m (<= 8): weight-bandwidth bound

@@ -111,13 +111,32 @@ est = RefEstimator(cfg)
 est.build(db, 'all')
 out['est.ref_imgs0'] = est.ref_info['imgs'][:2]
 out['est.ref_poses'] = est.ref_info['poses']
-q_id = EST['query_id']
+# pick a query frame whose selections are well separated (random weights give random margins;
+# parity of index selections is only meaningful when the reference's own margin is not ~0)
+refiner_saved, est.refiner = est.refiner, None
+q_id = None
+for cand in syn.get_img_ids():
+    _, it = est.predict(syn.get_image(cand), syn.get_K(cand))
+    sc = np.sort(it['sel_scores'])
+    print('candidate', cand, 'selector margin', sc[-1] - sc[-2], 'det scale', it['det_scale_r2q'])
+    if sc[-1] - sc[-2] > 0.15:
+        q_id = cand
+        break
+est.refiner = refiner_saved
+out['est.query_id'] = np.asarray(int(q_id))
 pose, inter = est.predict(syn.get_image(q_id), syn.get_K(q_id))
 out['est.det_position'], out['est.det_scale'] = inter['det_position'], inter['det_scale_r2q']
 out['est.sel_ref_idx'], out['est.sel_angle'] = np.asarray(inter['sel_ref_idx']), np.asarray(inter['sel_angle_r2q'])
 out['est.sel_scores'] = inter['sel_scores']
 out['est.refine_poses'] = np.stack(inter['refine_poses'], 0)
 out['est.pose'] = pose
+# tracking mode (predict.py:56-59 style): refinement only, from a perturbed ground-truth pose
+gt = syn.get_pose(q_id)
+init = np.concatenate([RP.quat2mat([0.997, 0.04, -0.03, 0.05]) @ gt[:, :3], gt[:, 3:] * 1.06], 1).astype(np.float32)
+pose_t, inter_t = est.predict(syn.get_image(q_id), syn.get_K(q_id), pose_init=init)
+out['est.track_init'] = init
+out['est.track_poses'] = np.stack(inter_t['refine_poses'], 0)
+print('tracking poses', out['est.track_poses'][-1])
 s = np.sort(inter['sel_scores'])
 print('estimator: det', inter['det_position'], inter['det_scale_r2q'], 'sel', inter['sel_ref_idx'], inter['sel_angle_r2q'],
       'sel margin', s[-1] - s[-2])

@@ -1,0 +1,110 @@
+"""The tcgen05 3xTF32 convolution (g6d_conv_tc) against torch fp32 CPU and against the FFMA
+path: it must be fp32-faithful (error ~1e-6 relative, not TF32's 1e-3)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+def g(seed):
+    gen = torch.Generator(device='cpu')
+    gen.manual_seed(seed)
+    return gen
+
+
+def nhwc(x):
+    nd = x.dim()
+    return x.permute(0, *range(2, nd), 1).contiguous().cuda()
+
+
+def nchw(x):
+    nd = x.dim()
+    return x.permute(0, nd - 1, *range(1, nd - 1)).contiguous().cpu()
+
+
+@pytest.fixture(scope='module')
+def ops():
+    from gen6d_b200 import ops
+    ops.require_cuda()
+    return ops
+
+
+def rel_err(a, b):
+    return float((a - b).abs().max() / b.abs().max())
+
+
+@pytest.mark.parametrize('B,H,W,cin,cout', [(1, 16, 16, 32, 32), (2, 17, 23, 64, 64), (1, 32, 40, 128, 256),
+                                            (3, 8, 8, 512, 48), (1, 60, 80, 64, 128), (5, 4, 4, 256, 256)])
+def test_tc_conv2d_matches_fp32(ops, B, H, W, cin, cout):
+    x = torch.randn(B, cin, H, W, generator=g(1)) + 0.5
+    w = torch.randn(cout, cin, 3, 3, generator=g(2)) * (2 / (9 * cin)) ** .5
+    b = torch.randn(cout, generator=g(3))
+    ref = F.relu(F.conv2d(x.double(), w.double(), b.double(), padding=1)).float()
+    pc = ops.pack_conv(w.cuda(), b.cuda(), pad=1)
+    assert pc.w_hi is not None
+    os.environ['G6D_CONV_PATH'] = 'tc'
+    y_tc = nchw(ops.conv(nhwc(x), pc, act=ops.ACT_RELU))
+    os.environ['G6D_CONV_PATH'] = 'ffma'
+    y_ff = nchw(ops.conv(nhwc(x), pc, act=ops.ACT_RELU))
+    os.environ['G6D_CONV_PATH'] = 'tc'
+    e_tc, e_ff = rel_err(y_tc, ref), rel_err(y_ff, ref)
+    print(f'rel err vs fp64: tc {e_tc:.2e} ffma {e_ff:.2e}')
+    assert e_tc < 5e-6, e_tc          # fp32-faithful (plain TF32 would be ~5e-4)
+    assert e_ff < 5e-6
+
+
+@pytest.mark.parametrize('stride', [1, 2])
+def test_tc_conv3d(ops, stride):
+    x = torch.randn(2, 64, 8, 8, 8, generator=g(4))
+    w = torch.randn(128, 64, 3, 3, 3, generator=g(5)) * (2 / (27 * 64)) ** .5
+    b = torch.randn(128, generator=g(6))
+    ref = F.conv3d(x.double(), w.double(), b.double(), stride=stride, padding=1).float()
+    y = nchw(ops.conv(nhwc(x), ops.pack_conv(w.cuda(), b.cuda(), stride=stride, pad=1)))
+    assert rel_err(y, ref) < 5e-6
+
+
+def test_tc_splitk_correlation(ops):
+    q = torch.randn(1, 512, 12, 16, generator=g(7)).abs()
+    r = torch.randn(32, 512, 15, 15, generator=g(8)).abs()
+    ref = F.conv2d(q.double(), r.double(), padding=7).float()
+    rk = r.permute(0, 2, 3, 1).contiguous().cuda()
+    flat = rk.reshape(32, -1)
+    pc = ops.PackedConv(ops.transpose_to_packed(flat), None, 512, 32, (1, 15, 15), 1, (0, 7, 7))
+    pc.w_hi, pc.w_lo = ops.split_tf32(flat)
+    y = nchw(ops.conv(nhwc(q), pc))
+    assert rel_err(y, ref) < 5e-6
+
+
+@pytest.mark.parametrize('relu', [False, True])
+def test_tc_affine_prologue(ops, relu):
+    x = torch.randn(3, 64, 10, 12, generator=g(12)) * 2 + 1
+    w = torch.randn(32, 64, 3, 3, generator=g(13)) * 0.05
+    xn = F.instance_norm(x.double())
+    xn = F.relu(xn) if relu else xn
+    ref = F.conv2d(xn, w.double(), None, padding=1).float()
+    xc = nhwc(x)
+    ps, pb = ops.instnorm_stats(xc, rows_per_group=10 * 12)
+    y = ops.conv(xc, ops.pack_conv(w.cuda(), None, pad=1), prologue=ops.PRO_AFFINE_RELU if relu else ops.PRO_AFFINE,
+                 pro_scale=ps, pro_shift=pb, group_rows=1)
+    assert rel_err(nchw(y), ref) < 2e-5
+
+
+def test_tc_corr_prologue_and_channel_offsets(ops):
+    """Selector first-tower conv: x*scale[pos,c] + shift[c] on in-bounds taps; output into a concat buffer."""
+    S, h, w_, cin, cout = 6, 8, 8, 512, 64
+    x = torch.rand(S, cin, h, w_, generator=g(20))
+    scale = torch.rand(h * w_, cin, generator=g(21)) + 0.5
+    shift = torch.randn(cin, generator=g(22)) * 0.1
+    wt = torch.randn(cout, cin, 1, 3, 3, generator=g(23)) * 0.02
+    b = torch.randn(cout, generator=g(24))
+    xs = x.double() * scale.T.reshape(1, cin, h, w_).double() + shift.reshape(1, cin, 1, 1).double()
+    ref = F.conv2d(xs, wt[:, :, 0].double(), b.double(), padding=1).float()
+    out = torch.zeros(S, h, w_, 192, device='cuda')
+    ops.conv(nhwc(x), ops.pack_conv(wt.cuda(), b.cuda(), pad=(0, 1, 1)), prologue=ops.PRO_CORR, pro_scale=scale.cuda(),
+             pro_shift=shift.cuda(), group_rows=S, out=out, out_coff=64)
+    assert rel_err(nchw(out[..., 64:128].contiguous()), ref) < 5e-6
+    assert float(out[..., :64].abs().max()) == 0 and float(out[..., 128:].abs().max()) == 0

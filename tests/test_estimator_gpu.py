@@ -27,7 +27,7 @@ def test_build_matches_reference(est):
 
 def test_predict_matches_reference(est):
     e, db = est
-    q = cases.estimator_case()['query_id']
+    q = str(int(E['est.query_id']))
     pose, inter = e.predict(db.get_image(q), db.get_K(q))
     s = np.sort(E['est.sel_scores'])
     print('reference selector margin', s[-1] - s[-2])
@@ -35,9 +35,25 @@ def test_predict_matches_reference(est):
     np.testing.assert_allclose(inter['det_scale_r2q'], E['est.det_scale'], rtol=5e-3)
     assert int(inter['sel_ref_idx']) == int(E['est.sel_ref_idx'])                               # bit-exact viewpoint
     np.testing.assert_allclose(inter['sel_angle_r2q'], E['est.sel_angle'], atol=2e-2)
-    got = np.stack(inter['refine_poses'], 0)
-    want = E['est.refine_poses']
-    # rotations to 2e-2 (the chain detection->crop->selection->3x refinement amplifies fp32
-    # accumulation-order noise), translations relative to the object distance
-    np.testing.assert_allclose(got[:, :, :3], want[:, :, :3], atol=2e-2)
-    np.testing.assert_allclose(got[:, :, 3], want[:, :, 3], rtol=2e-2, atol=0.2)
+    # The pose handed to the refiner (detection + selection + similarity->pose) must agree.  The
+    # refined poses of THIS chain are not compared: with random weights the detector's scale is
+    # ~0.07, the implied object distance is ~40x off, the refiner then looks at featureless
+    # background and its InstanceNorms (1/sqrt(var + 1e-5) on near-constant channels) amplify fp32
+    # summation-order noise without bound.  Refinement parity is checked on a well-posed input in
+    # test_tracking_refinement_matches_reference and at tensor level in test_networks_gpu.py.
+    got, want = inter['refine_poses'][0], E['est.refine_poses'][0]
+    np.testing.assert_allclose(got[:, :3], want[:, :3], atol=5e-3)
+    np.testing.assert_allclose(got[:, 3], want[:, 3], rtol=5e-3, atol=5e-2)
+
+
+def test_tracking_refinement_matches_reference(est):
+    """predict(pose_init=...) = three refinement iterations from a perturbed ground-truth pose."""
+    e, db = est
+    q = str(int(E['est.query_id']))
+    pose, inter = e.predict(db.get_image(q), db.get_K(q), pose_init=E['est.track_init'])
+    got, want = np.stack(inter['refine_poses'], 0), E['est.track_poses']
+    err_r = np.abs(got[:, :, :3] - want[:, :, :3]).reshape(len(got), -1).max(1)
+    err_t = np.abs(got[:, :, 3] - want[:, :, 3]).max(1) / np.linalg.norm(want[:, :, 3], axis=1)
+    print('per-iteration max |dR|', err_r, 'relative |dt|', err_t)
+    np.testing.assert_allclose(got[:, :, :3], want[:, :, :3], atol=1e-2)
+    assert (err_t < 1e-2).all()

@@ -65,8 +65,8 @@ def test_detector_raw_correlation(det):
     que01 = ops.preprocess_u8(torch.from_numpy(c['que_imgs']).cuda(), out_c=3, imagenet_norm=False)
     got = net._raw_correlation(que01)
     for l, (a, b) in enumerate(zip(got, want)):
-        close(to_nchw(a), b, rtol=2e-5, atol=0.5)       # values ~1e5: 2e-5 relative
-        close(to_nchw(a), G[f'det.raw_corr{l}'], rtol=2e-5, atol=0.5)
+        close(to_nchw(a), b, rtol=3e-5, atol=0.5)       # values ~1e5; K = 115200 same-sign terms
+        close(to_nchw(a), G[f'det.raw_corr{l}'], rtol=3e-5, atol=0.5)
 
 
 def test_detector_maps_argmax_positions(det):
@@ -105,7 +105,7 @@ def test_selector_reference_cache(sel):
     for ours, want in zip(net.ref_feats_cache, feats):
         h, w, f = ours.shape[1:]
         ours_ = ours.reshape(rfn, an, h, w, f).permute(1, 0, 4, 2, 3)     # -> an,rfn,f,h,w
-        close(ours_, want, atol=2e-6)
+        close(ours_, want, atol=1e-5)     # L2-normalised VGG features through 8 tensor-core (3xTF32) convs
     close(net.ref_pose_embed, embed, atol=1e-5)
 
 
