@@ -44,6 +44,8 @@ _SIGNATURES = {
     'g6d_avgpool_affine': [P, P, L, I, I, L, P, P, I, P],
     'g6d_add': [P, P, P, L, P],
     'g6d_instnorm_stats': [P, L, I, I, I, L, F, P, P, P, P],
+    'g6d_instnorm_partial': [P, L, I, I, I, L, P, P],
+    'g6d_instnorm_finalize': [P, L, I, L, F, P, P, P],
     'g6d_conv': [C.POINTER(ConvDesc), P, P, P, P, P, P, P, P],
     'g6d_conv_workspace_bytes': [C.POINTER(ConvDesc)],
     'g6d_pack_conv_weight': [P, P, I, I, I, I, P, P],

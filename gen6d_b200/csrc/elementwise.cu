@@ -345,17 +345,11 @@ extern "C" int g6d_add(const float* a, const float* b, float* out, long long n, 
     return G6D_OK;
 }
 
-extern "C" int g6d_instnorm_stats(const float* x, long long rows, int C, int cstride, int coff,
-                                  long long rows_per_group, float eps, float* scale, float* shift, double* ws,
-                                  g6d_stream_t stream) {
-    G6D_REQUIRE(x && scale && shift && ws && rows > 0 && C > 0 && rows_per_group > 0 && rows % rows_per_group == 0 &&
-                    coff + C <= cstride,
-                "g6d_instnorm_stats: bad args");
+static int instnorm_partial_impl(const float* x, long long rows, int C, int cstride, int coff, long long rows_per_group,
+                                 double* ws, cudaStream_t st) {
     const long long groups = rows / rows_per_group;
-    G6D_REQUIRE(groups <= 65535, "g6d_instnorm_stats: too many groups");
-    cudaStream_t st = as_stream(stream);
     cudaError_t e = cudaMemsetAsync(ws, 0, sizeof(double) * 2 * groups * C, st);
-    if (e != cudaSuccess) { set_error("g6d_instnorm_stats: memset failed: %s", cudaGetErrorString(e)); return G6D_ECUDA; }
+    if (e != cudaSuccess) { set_error("g6d_instnorm: memset failed: %s", cudaGetErrorString(e)); return G6D_ECUDA; }
     // enough blocks per group to fill the machine, at least 32 rows each
     long long want = (4ll * kNumSMs + groups - 1) / groups;
     long long rpb = (rows_per_group + want - 1) / want;
@@ -365,7 +359,34 @@ extern "C" int g6d_instnorm_stats(const float* x, long long rows, int C, int cst
     in_stats_partial_kernel<<<dim3(bx, (unsigned)groups), threads, 0, st>>>(x, rows, C, cstride, coff, rows_per_group,
                                                                            (int)rpb, ws);
     G6D_CHECK_LAUNCH("g6d_instnorm_stats(partial)");
-    in_stats_final_kernel<<<ceil_div(groups * C, 256), 256, 0, st>>>(ws, groups * C, rows_per_group, eps, scale, shift);
+    return G6D_OK;
+}
+
+extern "C" int g6d_instnorm_partial(const float* x, long long rows, int C, int cstride, int coff,
+                                    long long rows_per_group, double* ws, g6d_stream_t stream) {
+    G6D_REQUIRE(x && ws && rows > 0 && C > 0 && rows_per_group > 0 && rows % rows_per_group == 0 && coff + C <= cstride,
+                "g6d_instnorm_partial: bad args");
+    G6D_REQUIRE(rows / rows_per_group <= 65535, "g6d_instnorm_partial: too many groups");
+    return instnorm_partial_impl(x, rows, C, cstride, coff, rows_per_group, ws, as_stream(stream));
+}
+
+extern "C" int g6d_instnorm_finalize(const double* ws, long long groups, int C, long long count, float eps,
+                                     float* scale, float* shift, g6d_stream_t stream) {
+    G6D_REQUIRE(ws && scale && shift && groups > 0 && C > 0 && count > 0, "g6d_instnorm_finalize: bad args");
+    in_stats_final_kernel<<<ceil_div(groups * C, 256), 256, 0, as_stream(stream)>>>(ws, groups * C, count, eps, scale, shift);
     G6D_CHECK_LAUNCH("g6d_instnorm_stats(final)");
     return G6D_OK;
+}
+
+extern "C" int g6d_instnorm_stats(const float* x, long long rows, int C, int cstride, int coff,
+                                  long long rows_per_group, float eps, float* scale, float* shift, double* ws,
+                                  g6d_stream_t stream) {
+    G6D_REQUIRE(x && scale && shift && ws && rows > 0 && C > 0 && rows_per_group > 0 && rows % rows_per_group == 0 &&
+                    coff + C <= cstride,
+                "g6d_instnorm_stats: bad args");
+    const long long groups = rows / rows_per_group;
+    G6D_REQUIRE(groups <= 65535, "g6d_instnorm_stats: too many groups");
+    int rc = instnorm_partial_impl(x, rows, C, cstride, coff, rows_per_group, ws, as_stream(stream));
+    if (rc != G6D_OK) return rc;
+    return g6d_instnorm_finalize(ws, groups, C, rows_per_group, eps, scale, shift, stream);
 }

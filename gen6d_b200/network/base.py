@@ -4,6 +4,7 @@ import torch
 import torch.nn as nn
 
 from .. import ops
+from ..graphs import StageCache
 
 
 IO_BYTES = {'h2d': 0, 'd2h': 0}   # bytes moved through the numpy-facing API (bench.py reads this)
@@ -17,13 +18,16 @@ class PackedModule(nn.Module):
     def __init__(self):
         super().__init__()
         self._packed = None
+        self.stages = StageCache()      # CUDA graphs of the fixed-shape numpy-API stages
         self.register_load_state_dict_post_hook(lambda module, keys: module.invalidate_packed())
 
     def invalidate_packed(self):
         self._packed = None
+        self.stages.clear()
 
     def _apply(self, fn, *args, **kwargs):
         self._packed = None
+        self.stages.clear()
         return super()._apply(fn, *args, **kwargs)
 
     @property

@@ -62,6 +62,7 @@ class Detector(PackedModule):
                 pc.w_hi, pc.w_lo = ops.split_tf32(flat)
             kernels.append(pc)
         self.ref_kernels = kernels
+        self.stages.clear()             # captured graphs hold pointers to the previous reference set
 
     def scale_sizes(self, hq, wq):
         """detector.py:236-239: round(h * 2**s), rounded UP to a multiple of 32."""
@@ -107,6 +108,12 @@ class Detector(PackedModule):
             outs['scores_feats'] = feats
         return outs
 
+    def _detect_u8(self, u8):
+        """uint8 frame(s) on the device -> [qn,4] (x, y, scale, score); one capturable stage."""
+        o = self._detect_nhwc(ops.preprocess_u8(u8, out_c=3, imagenet_norm=False))
+        out, _ = ops.det_parse(o['score_predict'], o['scale_predict'], o['offset_predict'], self.pool_ratio)
+        return out
+
     # ------------------------------------------------------------------ reference tensor API (NCHW)
     def load_impl(self, ref_imgs):
         with torch.no_grad():
@@ -138,8 +145,6 @@ class Detector(PackedModule):
     def detect_que_imgs(self, que_imgs):
         """@param que_imgs: uint8 [qn,h,w,3] -> {'positions': f32 [qn,2], 'scales': f32 [qn]} (detector.py:291-304)"""
         with torch.no_grad():
-            u8 = self._to_dev(que_imgs)
-            o = self._detect_nhwc(ops.preprocess_u8(u8, out_c=3, imagenet_norm=False))
-            out, _ = ops.det_parse(o['score_predict'], o['scale_predict'], o['offset_predict'], self.pool_ratio)
+            out = self.stages.run('detect', self._detect_u8, [self._to_dev(que_imgs)])
             out = self._to_host(out)
         return {'positions': out[:, :2].copy(), 'scales': out[:, 2].copy()}

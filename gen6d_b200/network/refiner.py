@@ -133,6 +133,12 @@ class VolumeRefiner(PackedModule):
             return out, {'mean_in': mean_in, 'std': stdv, 'feats': feats, 'encoded': enc}
         return out
 
+    def _refine_u8(self, que_u8, que_K, que_pose, ref_u8, ref_Ks, ref_poses):
+        """uint8 crops + cameras on the device -> [qn,7]; one capturable stage."""
+        que = ops.preprocess_u8(que_u8, out_c=4, imagenet_norm=True)
+        ref = ops.preprocess_u8(ref_u8, out_c=4, imagenet_norm=True)
+        return self._forward_nhwc(que, que_K, que_pose, ref, ref_Ks, ref_poses)
+
     # ------------------------------------------------------------------ reference tensor API
     def forward(self, data):
         """data['que_imgs_info']: imgs [qn,3,h,w], Ks_in [qn,3,3], poses_in [qn,3,4];
@@ -159,9 +165,6 @@ class VolumeRefiner(PackedModule):
         from .. import geometry as G
         prob = G.refine_problem(self.ref_database, self.ref_ids, que_img, que_K, in_pose, size, ref_num, ref_even)
         with torch.no_grad():
-            que = ops.preprocess_u8(self._to_dev(prob['que_img'][None]), out_c=4, imagenet_norm=True)
-            ref = ops.preprocess_u8(self._to_dev(prob['ref_imgs'][None]), out_c=4, imagenet_norm=True)
-            out = self._forward_nhwc(que, self._to_dev(prob['que_K'][None]), self._to_dev(prob['que_pose'][None]), ref,
-                                     self._to_dev(prob['ref_Ks'][None]), self._to_dev(prob['ref_poses'][None]))
-            out = self._to_host(out)[0]
+            args = [self._to_dev(prob[k][None]) for k in ('que_img', 'que_K', 'que_pose', 'ref_imgs', 'ref_Ks', 'ref_poses')]
+            out = self._to_host(self.stages.run('refine', self._refine_u8, args))[0]
         return G.apply_refinement(prob, quat=out[:4], offset=out[4:6], scale=2.0 ** out[6])

@@ -17,6 +17,22 @@ from .base import PackedModule, linear_as_conv
 from .params import SEL_TOWER_POST, SEL_TOWERS, VGG11BNParams, selector_modules
 
 IN_EPS = 1e-5
+
+
+class LocalComm:
+    """Single-process stand-in for gen6d_b200.dist.Comm (no sharding)."""
+    rank, world = 0, 1
+
+    def all_reduce_sum(self, t):
+        return t
+
+    def all_gather_cat(self, t, dim=0):
+        return t
+
+    def shard_range(self, n):
+        return 0, n
+
+
 FEAT_PAD = 516  # 512 correlation features + 3 similarity scores, padded to a multiple of 4
 
 
@@ -29,10 +45,12 @@ class ViewpointSelector(PackedModule):
         self.backbone = VGG11BNParams()
         for name, mod in selector_modules(self.cfg['selector_angle_num']).items():
             setattr(self, name, mod)
-        self.ref_feats_cache = None   # 3 x [S, h, w, 512]
-        self.ref_sums = None          # per level (sum, sum of squares) over S, float64 [h*w, 512]
-        self.ref_pose_embed = None    # [rfn, 512]
-        self.ref_shape = None         # (rfn, an)
+        self.ref_feats_cache = None   # 3 x [S_local, h, w, 512]
+        self.ref_sums = None          # per level (sum, sum of squares) over ALL S, float64 [h*w, 512]
+        self.ref_pose_embed = None    # [rfn_local, 512]
+        self.ref_shape = None         # (rfn_local, an)
+        self.rfn_total = None         # references over all shards
+        self.comm = LocalComm()       # gen6d_b200.dist.Comm when the reference axis is sharded over GPUs
 
     # ------------------------------------------------------------------ weights
     def _pack(self):
@@ -90,22 +108,39 @@ class ViewpointSelector(PackedModule):
         return cam / torch.clamp(torch.linalg.norm(cam, dim=1, keepdim=True), min=1e-12)
 
     def _load_nhwc(self, ref_norm4, rfn, an, ref_poses, object_center, object_vert, chunk=64):
-        """ref_norm4: [S = rfn*an (r-major), h, w, 4] ImageNet-normalised (selector.py:121-148)."""
+        """ref_norm4: [S = rfn*an (r-major), h, w, 4] ImageNet-normalised (selector.py:121-148).
+        With a sharded comm every rank is handed the full set and keeps references [r0, r1)."""
         p = self.packed()
+        self.rfn_total = rfn
+        r0, r1 = self.comm.shard_range(rfn)
+        ref_norm4 = ref_norm4[r0 * an:r1 * an]
+        vp_all = self.viewpoints(ref_poses, object_center, object_vert)   # frame anchored on GLOBAL ref 0
+        rfn = r1 - r0
         S = rfn * an
         levels = [[], [], []]
         for s0 in range(0, S, chunk):
             for l, f in enumerate(self._feats(ref_norm4[s0:s0 + chunk])):
                 levels[l].append(f)
         self.ref_feats_cache = [torch.cat(lv, 0) if len(lv) > 1 else lv[0] for lv in levels]
-        self.ref_sums = [ops.sel_ref_sums(f.reshape(S, -1, f.shape[-1])) for f in self.ref_feats_cache]
+        sums = [ops.sel_ref_sums(f.reshape(S, -1, f.shape[-1])) for f in self.ref_feats_cache]
+        # closed-form first-InstanceNorm statistics need the sums over ALL references: one all-reduce at load
+        self.ref_sums = [(self.comm.all_reduce_sum(a), self.comm.all_reduce_sum(b)) for a, b in sums]
         self.ref_shape = (rfn, an)
         vp = torch.zeros(rfn, 4, dtype=torch.float32)
-        vp[:, :3] = self.viewpoints(ref_poses, object_center, object_vert)
+        vp[:, :3] = vp_all[r0:r1]
         x = vp.to(self.device).reshape(rfn, 1, 1, 4)
         for i, pc in enumerate(p['vpe']):
             x = ops.conv(x, pc, act=ops.ACT_RELU if i < 2 else ops.ACT_NONE)
         self.ref_pose_embed = x.reshape(rfn, 512)
+        self.stages.clear()             # captured graphs hold pointers to the previous reference set
+
+    def _stats(self, y, rows_local, rows_total):
+        """InstanceNorm statistics over a group that may span GPUs: local (sum, sum-of-squares) in
+        fp64, all-reduced, then scale = rstd, shift = -mean*rstd (exact, not per-shard)."""
+        if self.comm.world == 1:
+            return ops.instnorm_stats(y, rows_per_group=rows_local, eps=IN_EPS)
+        ws = self.comm.all_reduce_sum(ops.instnorm_partial(y, rows_per_group=rows_local))
+        return ops.instnorm_finalize(ws, rows_total, IN_EPS)
 
     def _tower(self, level, ref, scale, shift, cat_buf, S):
         """corr_conv_list[level] (selector.py:27-69) on the implicit correlation volume."""
@@ -120,7 +155,8 @@ class ViewpointSelector(PackedModule):
             # InstanceNorm3d statistics over (S, h, w) of the raw conv output; the normalisation
             # itself (and the ReLU) is applied by the next conv's loader.  MaxPool commutes with
             # the positive-slope affine, so pooling the raw tensor first is exact.
-            ps, pb = ops.instnorm_stats(y, rows_per_group=y.numel() // y.shape[-1], eps=IN_EPS)
+            rows = y.numel() // y.shape[-1]
+            ps, pb = self._stats(y, rows, rows // self.ref_shape[0] * self.rfn_total)
             pro = ops.PRO_AFFINE_RELU if 'r' in post else ops.PRO_AFFINE
             x = ops.maxpool2x2(y) if 'p' in post else y
 
@@ -129,6 +165,7 @@ class ViewpointSelector(PackedModule):
         p = self.packed()
         rfn, an = self.ref_shape
         S = rfn * an
+        S_total = self.rfn_total * an
         dev = self.device
         cat_buf = torch.empty(S, 4, 4, 768, device=dev, dtype=torch.float32)
         feats = torch.zeros(S, FEAT_PAD, device=dev, dtype=torch.float32)
@@ -137,18 +174,29 @@ class ViewpointSelector(PackedModule):
             h, w, c = q.shape
             q2 = q.reshape(h * w, c)
             ops.sel_corr_score(ref.reshape(S, h * w, c), q2, out=scores[l])
-            scale, shift = ops.sel_corr_prologue(q2, s1, s2, S, IN_EPS)
+            scale, shift = ops.sel_corr_prologue(q2, s1, s2, S_total, IN_EPS)
             self._tower(l, ref, scale, shift, cat_buf, S)
         # corr_feats_conv (selector.py:71-77): 1x1 768->512, IN, ReLU, 1x1 512->512, AvgPool(4,4).
         # The second 1x1 conv is linear, so the 4x4 average is taken first (16x less work).
         y = ops.conv(cat_buf, p['cf0'])
-        ps, pb = ops.instnorm_stats(y, rows_per_group=S * 16, eps=IN_EPS)
+        ps, pb = self._stats(y, S * 16, S_total * 16)
         y = ops.avgpool_affine(y.reshape(S * 16, 512), 16, ps, pb, rows_per_group=S * 16, act=ops.ACT_RELU)
         ops.conv(y.reshape(S, 1, 1, 512), p['cf3'], out=feats.reshape(S, 1, 1, FEAT_PAD), out_coff=0)
-        ops.sel_vp_norm(scores, feats, 512, IN_EPS)                     # vp_norm, selector.py:201
+        if self.comm.world == 1:
+            ops.sel_vp_norm(scores, feats, 512, IN_EPS)                 # vp_norm, selector.py:201
+        else:   # InstanceNorm2d over ALL (rfn, an): gather the 3*S_total scores, normalise, keep our rows
+            all_scores = self.comm.all_gather_cat(scores, dim=1).contiguous()
+            tmp = torch.zeros(S_total, 4, device=dev, dtype=torch.float32)
+            ops.sel_vp_norm(all_scores, tmp, 0, IN_EPS)
+            r0, _ = self.comm.shard_range(self.rfn_total)
+            feats[:, 512:515] = tmp[r0 * an:r0 * an + S, :3]
         x = ops.conv(feats.reshape(S, 1, 1, FEAT_PAD), p['sp0'], act=ops.ACT_RELU)
         x = ops.conv(x, p['sp2']).reshape(rfn, an, 512)
         sf = ops.sel_max_angle_add(x, self.ref_pose_embed)              # selector.py:203-204
+        # everything below couples all references (attention, InstanceNorm1d over rfn): gather the
+        # per-reference score features once ([rfn,512] = 128 KB at 64 refs) and run the tail replicated
+        sf = self.comm.all_gather_cat(sf, dim=0).contiguous()
+        rfn_local, rfn = rfn, self.rfn_total
         for att, (m0, m3) in zip(p['atts'], p['mlps']):
             x4 = sf.reshape(rfn, 1, 1, 512)
             qv = ops.conv(x4, att['conv_query']).reshape(rfn, 512)
@@ -165,10 +213,11 @@ class ViewpointSelector(PackedModule):
             sf = ops.add(y, sf)
         x = ops.conv(sf.reshape(rfn, 1, 1, 512), p['score_predict'][0], act=ops.ACT_RELU)
         logits = ops.conv(x, p['score_predict'][1]).reshape(rfn)
-        x = feats.reshape(rfn, 1, 1, an * FEAT_PAD)
+        x = feats.reshape(rfn_local, 1, 1, an * FEAT_PAD)               # angles are per-reference: local
         for i, pc in enumerate(p['angle_predict']):
             x = ops.conv(x, pc, act=ops.ACT_RELU if i < 2 else ops.ACT_NONE)
-        return logits, x.reshape(rfn), scores
+        angles = self.comm.all_gather_cat(x.reshape(rfn_local), dim=0)
+        return logits, angles, scores
 
     def _select_nhwc(self, que_norm4):
         if self.ref_feats_cache is None:
@@ -181,6 +230,12 @@ class ViewpointSelector(PackedModule):
             angles.append(ang)
             taps.append(sc)
         return torch.stack(logits, 0), torch.stack(angles, 0), torch.stack(taps, 0)
+
+    def _select_u8(self, u8):
+        """uint8 crop(s) on the device -> (ref_idx [qn], (angle, logit) [qn,2], logits [qn,rfn])."""
+        logits, angles, _ = self._select_nhwc(ops.preprocess_u8(u8, out_c=4, imagenet_norm=True))
+        idx, out = ops.sel_parse(logits, angles)
+        return idx, out, logits
 
     # ------------------------------------------------------------------ reference tensor API
     def extract_ref_feats(self, ref_imgs, ref_poses, object_center, object_vert, is_train=False):
@@ -221,8 +276,10 @@ class ViewpointSelector(PackedModule):
         """@param que_imgs: uint8 [qn,h,w,3] -> {'ref_idx': i64 [qn], 'angles': f32 [qn], 'scores': f32 [qn,rfn]}
         (selector.py:165-175; the angle is returned un-rescaled, as the reference does)"""
         with torch.no_grad():
-            x = ops.preprocess_u8(self._to_dev(que_imgs), out_c=4, imagenet_norm=True)
-            logits, angles, _ = self._select_nhwc(x)
-            idx, out = ops.sel_parse(logits, angles)
+            u8 = self._to_dev(que_imgs)
+            if self.comm.world == 1:
+                idx, out, logits = self.stages.run('select', self._select_u8, [u8])
+            else:
+                idx, out, logits = self._select_u8(u8)      # collectives inside: run eagerly
             idx, out, logits = self._to_host(idx), self._to_host(out), self._to_host(logits)
         return {'ref_idx': idx, 'angles': out[:, 0].copy(), 'scores': logits}

@@ -137,6 +137,26 @@ def instnorm_stats(x, rows_per_group, channels=None, coff=0, eps=1e-5):
     return scale, shift
 
 
+def instnorm_partial(x, rows_per_group, channels=None, coff=0):
+    """Per (group, channel) (sum, sum of squares) as float64 [groups, C, 2] -- all-reducible across GPUs."""
+    cstride = x.shape[-1]
+    Cc = channels or cstride
+    rows = x.numel() // cstride
+    groups = rows // rows_per_group
+    ws = torch.empty(groups, Cc, 2, device=x.device, dtype=torch.float64)
+    _call('g6d_instnorm_partial', _p(x), rows, Cc, cstride, coff, rows_per_group, _p(ws, torch.float64), _stream())
+    return ws
+
+
+def instnorm_finalize(ws, count, eps=1e-5):
+    """ws [groups, C, 2] (after any cross-rank reduction), count = rows per group over all ranks."""
+    groups, Cc, _ = ws.shape
+    scale = torch.empty(groups, Cc, device=ws.device, dtype=torch.float32)
+    shift = torch.empty_like(scale)
+    _call('g6d_instnorm_finalize', _p(ws, torch.float64), groups, Cc, count, eps, _p(scale), _p(shift), _stream())
+    return scale, shift
+
+
 def affine_act(x, scale, shift, rows_per_group, act=ACT_NONE, channels=None, in_coff=0, out=None, out_coff=0):
     ics = x.shape[-1]
     Cc = channels or ics

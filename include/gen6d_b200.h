@@ -88,6 +88,14 @@ int g6d_add(const float* a, const float* b, float* out, long long n, g6d_stream_
 int g6d_instnorm_stats(const float* x, long long rows, int C, int cstride, int coff, long long rows_per_group,
                        float eps, float* scale, float* shift, double* ws, g6d_stream_t stream);
 
+/* The two halves of g6d_instnorm_stats, for statistics that span GPUs (reference-sharded selector):
+ * partial writes ws[g,c] = (sum, sum of squares) as doubles; the caller all-reduces ws across ranks;
+ * finalize turns it into scale/shift with `count` = total rows per group over all ranks. */
+int g6d_instnorm_partial(const float* x, long long rows, int C, int cstride, int coff, long long rows_per_group,
+                         double* ws, g6d_stream_t stream);
+int g6d_instnorm_finalize(const double* ws, long long groups, int C, long long count, float eps, float* scale,
+                          float* shift, g6d_stream_t stream);
+
 /* ------------------------------------------------------------------ convolution ------------ */
 typedef struct g6d_conv_desc {
     int B, D, H, W, Cin;      /* input [B,D,H,W,*]; channels [in_coff, in_coff+Cin) of rows in_cstride wide */
