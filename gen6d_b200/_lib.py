@@ -62,6 +62,7 @@ _SIGNATURES = {
     'g6d_sel_ref_sums': [P, I, I, I, P, P, P],
     'g6d_sel_corr_prologue': [P, P, P, I, I, I, F, P, P, P],
     'g6d_sel_corr_score': [P, P, I, I, I, P, P],
+    'g6d_sel_corr_score3': [P, P, P, P, P, P, I, I, I, I, I, P, P, P],
     'g6d_sel_vp_norm': [P, I, I, F, P, I, I, P],
     'g6d_sel_max_angle_add': [P, P, P, I, I, I, P],
     'g6d_attention': [P, P, P, P, I, I, I, P],

@@ -12,122 +12,145 @@ struct VolParams {
     int Q, R, fh, fw, C, sn, img_h, img_w;
 };
 
-// grid_sample(bilinear, zeros padding, align_corners=False) tap set for one projected point
-struct Taps {
-    int idx[4];     // feature-map linear index (y*fw + x) or -1 when the tap is out of bounds
-    float w[4];
-};
+// ---- volume fill, v2 -------------------------------------------------------------------------
+// A CTA (8 warps) owns a 2x4x8 brick of voxels so that the bilinear footprints of its voxels
+// overlap in L1; a warp processes 4 consecutive voxels (along k) at a time:
+//   phase A  lane = (view, voxel-in-quad): ONE projection + tap set per (voxel, view) pair,
+//            28 of 32 lanes busy (6 refs + query), instead of every lane recomputing all views;
+//   phase B  per voxel: the 4 taps of each view are broadcast with warp shuffles and every lane
+//            gathers its 4 channels (128-bit, one 512 B feature row per tap per warp), then
+//            mean / unbiased two-pass std / query sample are written as full 512 B rows with
+//            streaming stores.
+// Feature maps (3.7 MB / pose) are L2/L1 resident; algorithmic HBM traffic is the 50 MB of output.
+// The floor of this formulation is the L1 gather: 28 taps x 512 B per voxel = 14 KB through a
+// 128 B/clk L1 -> ~13 us per pose on 148 SMs, above the 8.2 us pure-HBM time.
+constexpr int kViewsMax = kMaxRefViews;   // views = R references + the query (view index R) <= 8
 
-// P = K @ [R|t]  (refiner.py:227,243), then p = v @ P[:, :3]^T + P[:, 3] (refiner.py:195-197)
-__device__ __forceinline__ Taps make_taps(const float* __restrict__ K, const float* __restrict__ pose, float vx,
-                                          float vy, float vz, int fh, int fw, int img_h, int img_w) {
-    float P[12];
-#pragma unroll
-    for (int r = 0; r < 3; ++r)
-#pragma unroll
-        for (int c = 0; c < 4; ++c)
-            P[r * 4 + c] = fmaf(K[r * 3 + 0], pose[c], fmaf(K[r * 3 + 1], pose[4 + c], K[r * 3 + 2] * pose[8 + c]));
-    const float px = fmaf(vx, P[0], fmaf(vy, P[1], fmaf(vz, P[2], P[3])));
-    const float py = fmaf(vx, P[4], fmaf(vy, P[5], fmaf(vz, P[6], P[7])));
-    float pz = fmaf(vx, P[8], fmaf(vy, P[9], fmaf(vz, P[10], P[11])));
-    if (pz < 1e-4f) pz = 1e-4f;                       // refiner.py:199-200
-    const float u = px / pz, v = py / pz;
-    // normalize_coords (operator.py:4-17) with the IMAGE size, then grid_sample's unnormalise
-    // with the FEATURE size (align_corners=False): ix = ((g + 1) * W_f - 1) / 2
-    const float gx = ((u + 0.5f) / (float)img_w - 0.5f) * 2.f;
-    const float gy = ((v + 0.5f) / (float)img_h - 0.5f) * 2.f;
-    const float ix = ((gx + 1.f) * (float)fw - 1.f) * 0.5f;
-    const float iy = ((gy + 1.f) * (float)fh - 1.f) * 0.5f;
-    Taps t;
-    const float fx0 = floorf(ix), fy0 = floorf(iy);
-    const float lx = ix - fx0, ly = iy - fy0;
-    // keep the float->int conversion safe for huge coordinates (points behind the camera)
-    const bool near = (fx0 > -2.f) && (fx0 < (float)fw + 1.f) && (fy0 > -2.f) && (fy0 < (float)fh + 1.f);
-    const int x0 = near ? (int)fx0 : -10, y0 = near ? (int)fy0 : -10;
-    const int xs[2] = {x0, x0 + 1}, ys[2] = {y0, y0 + 1};
-    const float wx[2] = {1.f - lx, lx}, wy[2] = {1.f - ly, ly};
-#pragma unroll
-    for (int j = 0; j < 2; ++j)
-#pragma unroll
-        for (int i = 0; i < 2; ++i) {
-            const bool inb = (unsigned)xs[i] < (unsigned)fw && (unsigned)ys[j] < (unsigned)fh;
-            t.idx[j * 2 + i] = inb ? ys[j] * fw + xs[i] : -1;
-            t.w[j * 2 + i] = wx[i] * wy[j];
-        }
-    return t;
-}
+__global__ void __launch_bounds__(256, 3) ref_volume_fill_kernel(const VolParams p) {
+    __shared__ float sP[kViewsMax][12];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int sn = p.sn;
+    const int nbk = (sn + 7) / 8, nbj = (sn + 3) / 4, nbi = (sn + 1) / 2;
+    const int bricks = nbi * nbj * nbk;
+    const int qi = blockIdx.x / bricks;
+    int b = blockIdx.x % bricks;
+    const int bk = b % nbk; b /= nbk;
+    const int bj = b % nbj;
+    const int bi = b / nbj;
+    const int nviews = p.R + 1;
 
-__device__ __forceinline__ float4 sample4(const float* __restrict__ fmap, const Taps& t, int C, int c) {
-    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        if (t.idx[k] >= 0) {
-            const float4 v = __ldg(reinterpret_cast<const float4*>(fmap + (long long)t.idx[k] * C + c));
-            acc.x = fmaf(v.x, t.w[k], acc.x); acc.y = fmaf(v.y, t.w[k], acc.y);
-            acc.z = fmaf(v.z, t.w[k], acc.z); acc.w = fmaf(v.w, t.w[k], acc.w);
-        }
+    // P_v = K_v @ [R|t]_v for the R references and the query of this pose (refiner.py:227,243)
+    if (threadIdx.x < nviews * 12) {
+        const int v = threadIdx.x / 12, e = threadIdx.x % 12, r = e / 4, c = e % 4;
+        const float* K = v < p.R ? p.ref_Ks + ((long long)qi * p.R + v) * 9 : p.que_Ks + (long long)qi * 9;
+        const float* T = v < p.R ? p.ref_poses + ((long long)qi * p.R + v) * 12 : p.que_poses + (long long)qi * 12;
+        sP[v][e] = fmaf(K[r * 3 + 0], T[c], fmaf(K[r * 3 + 1], T[4 + c], K[r * 3 + 2] * T[8 + c]));
     }
-    return acc;
-}
+    __syncthreads();
 
-// One warp per voxel; lane l owns channels [4l, 4l+4) (+128 per extra pass for C > 128).
-// Projection + bilinear weights are recomputed by every lane (a few dozen FMAs, cheaper than a
-// shuffle broadcast).  The 7 feature maps (3.7 MB per pose) stay L2-resident; the HBM traffic
-// that matters is the 3*C*sn^3*4 B of output, written as full 512 B rows with streaming stores.
-__global__ void __launch_bounds__(256) ref_volume_fill_kernel(const VolParams p) {
-    const int lane = threadIdx.x & 31;
-    const long long warp_global = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const long long nvox = (long long)p.sn * p.sn * p.sn;
-    if (warp_global >= nvox * p.Q) return;
-    const int qi = (int)(warp_global / nvox);
-    const int vox = (int)(warp_global % nvox);
-    const int k = vox % p.sn, j = (vox / p.sn) % p.sn, i = vox / (p.sn * p.sn);
-    // torch.linspace(-1, 1, sn): start + step*idx for the first half, end - step*(n-1-idx) after
-    const float step = 2.f / (float)(p.sn - 1);
-    auto lin = [&](int a) { return a < p.sn / 2 ? -1.f + step * (float)a : 1.f - step * (float)(p.sn - 1 - a); };
-    const float ci = lin(i), cj = lin(j), ck = lin(k);
-    // row vector @ R_in  (refiner.py:216-220); R_in = poses_in[:, :3, :3]
+    const int my_view = lane >> 2, my_vox = lane & 3;
+    const bool proj_lane = my_view < nviews;
+    const float* P = sP[proj_lane ? my_view : 0];     // read from shared memory in phase A (keeps registers low)
     const float* qp = p.que_poses + (long long)qi * 12;
-    const float vx = fmaf(ci, qp[0], fmaf(cj, qp[4], ck * qp[8]));
-    const float vy = fmaf(ci, qp[1], fmaf(cj, qp[5], ck * qp[9]));
-    const float vz = fmaf(ci, qp[2], fmaf(cj, qp[6], ck * qp[10]));
-
+    const float r00 = qp[0], r01 = qp[1], r02 = qp[2], r10 = qp[4], r11 = qp[5], r12 = qp[6], r20 = qp[8], r21 = qp[9],
+                r22 = qp[10];
+    const float step = 2.f / (float)(sn - 1);
+    auto lin = [&](int a) { return a < sn / 2 ? -1.f + step * (float)a : 1.f - step * (float)(sn - 1 - a); };
     const long long fsz = (long long)p.fh * p.fw * p.C;
-    const long long orow = (long long)qi * nvox + vox;
-    for (int c = lane * 4; c < p.C; c += 128) {
-        float4 s[kMaxRefViews];
-        float4 mean = make_float4(0.f, 0.f, 0.f, 0.f);
+    const float* ref_base = p.ref_feats + (long long)qi * p.R * fsz;
+    const float* que_base = p.que_feats + (long long)qi * fsz;
+    const long long nvox = (long long)sn * sn * sn;
+
+    for (int qd = warp; qd < 16; qd += 8) {
+        const int i = bi * 2 + (qd >> 3), j = bj * 4 + ((qd >> 1) & 3), k0 = bk * 8 + (qd & 1) * 4;
+        if (i >= sn || j >= sn || k0 >= sn) continue;          // warp-uniform
+        // ---- phase A: this lane's (voxel, view) projection and bilinear tap set
+        int tidx[4]; float tw[4];
+        {
+            const int k = min(k0 + my_vox, sn - 1);
+            const float ci = lin(i), cj = lin(j), ck = lin(k);
+            // row vector @ R_in (refiner.py:216-220)
+            const float vx = fmaf(ci, r00, fmaf(cj, r10, ck * r20));
+            const float vy = fmaf(ci, r01, fmaf(cj, r11, ck * r21));
+            const float vz = fmaf(ci, r02, fmaf(cj, r12, ck * r22));
+            const float px = fmaf(vx, P[0], fmaf(vy, P[1], fmaf(vz, P[2], P[3])));
+            const float py = fmaf(vx, P[4], fmaf(vy, P[5], fmaf(vz, P[6], P[7])));
+            float pz = fmaf(vx, P[8], fmaf(vy, P[9], fmaf(vz, P[10], P[11])));
+            if (pz < 1e-4f) pz = 1e-4f;                               // refiner.py:199-200
+            const float u = px / pz, v = py / pz;
+            const float gx = ((u + 0.5f) / (float)p.img_w - 0.5f) * 2.f;   // operator.py:4-17
+            const float gy = ((v + 0.5f) / (float)p.img_h - 0.5f) * 2.f;
+            const float ix = ((gx + 1.f) * (float)p.fw - 1.f) * 0.5f;      // grid_sample, align_corners=False
+            const float iy = ((gy + 1.f) * (float)p.fh - 1.f) * 0.5f;
+            const float fx0 = floorf(ix), fy0 = floorf(iy);
+            const float lx = ix - fx0, ly = iy - fy0;
+            const bool close_by = (fx0 > -2.f) && (fx0 < (float)p.fw + 1.f) && (fy0 > -2.f) && (fy0 < (float)p.fh + 1.f);
+            const int x0 = close_by ? (int)fx0 : -10, y0 = close_by ? (int)fy0 : -10;
 #pragma unroll
-        for (int r = 0; r < kMaxRefViews; ++r) {
-            if (r < p.R) {
-                const long long v = (long long)qi * p.R + r;
-                const Taps t = make_taps(p.ref_Ks + v * 9, p.ref_poses + v * 12, vx, vy, vz, p.fh, p.fw, p.img_h, p.img_w);
-                s[r] = sample4(p.ref_feats + v * fsz, t, p.C, c);
-                mean.x += s[r].x; mean.y += s[r].y; mean.z += s[r].z; mean.w += s[r].w;
+            for (int t = 0; t < 4; ++t) {
+                const int xx = x0 + (t & 1), yy = y0 + (t >> 1);
+                const bool inb = proj_lane && (unsigned)xx < (unsigned)p.fw && (unsigned)yy < (unsigned)p.fh;
+                // out-of-bounds taps (zeros padding) keep a valid address and get weight 0, so the
+                // gather below is branch-free and all loads of a view can be in flight together
+                tidx[t] = inb ? (yy * p.fw + xx) * p.C : 0;
+                tw[t] = inb ? ((t & 1) ? lx : 1.f - lx) * ((t >> 1) ? ly : 1.f - ly) : 0.f;
             }
         }
-        const float fr = (float)p.R;
-        mean.x /= fr; mean.y /= fr; mean.z /= fr; mean.w /= fr;
-        float4 var = make_float4(0.f, 0.f, 0.f, 0.f);
+        // ---- phase B: gather + aggregate, one voxel at a time, all lanes on channels
+        for (int vq = 0; vq < 4; ++vq) {
+            const int k = k0 + vq;
+            if (k >= sn) break;                                        // warp-uniform
+            const long long orow = (long long)qi * nvox + ((long long)i * sn + j) * sn + k;
+            for (int c = lane * 4; c < p.C; c += 128) {
+                float4 s[kViewsMax];
+                float4 mean = make_float4(0.f, 0.f, 0.f, 0.f), qs = mean;
 #pragma unroll
-        for (int r = 0; r < kMaxRefViews; ++r) {
-            if (r < p.R) {
-                float d;
-                d = s[r].x - mean.x; var.x = fmaf(d, d, var.x);
-                d = s[r].y - mean.y; var.y = fmaf(d, d, var.y);
-                d = s[r].z - mean.z; var.z = fmaf(d, d, var.z);
-                d = s[r].w - mean.w; var.w = fmaf(d, d, var.w);
+                for (int v = 0; v < kViewsMax; ++v) {
+                    if (v < nviews) {
+                        const float* fmap = v < p.R ? ref_base + (long long)v * fsz : que_base;
+                        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+                        float4 f[4]; float w[4];
+#pragma unroll
+                        for (int t = 0; t < 4; ++t) {
+                            const int idx = __shfl_sync(0xffffffffu, tidx[t], v * 4 + vq);
+                            w[t] = __shfl_sync(0xffffffffu, tw[t], v * 4 + vq);
+                            f[t] = __ldg(reinterpret_cast<const float4*>(fmap + idx + c));
+                        }
+#pragma unroll
+                        for (int t = 0; t < 4; ++t) {
+                            acc.x = fmaf(f[t].x, w[t], acc.x); acc.y = fmaf(f[t].y, w[t], acc.y);
+                            acc.z = fmaf(f[t].z, w[t], acc.z); acc.w = fmaf(f[t].w, w[t], acc.w);
+                        }
+                        if (v < p.R) {
+                            s[v] = acc;
+                            mean.x += acc.x; mean.y += acc.y; mean.z += acc.z; mean.w += acc.w;
+                        } else {
+                            qs = acc;
+                        }
+                    }
+                }
+                const float fr = (float)p.R;
+                mean.x /= fr; mean.y /= fr; mean.z /= fr; mean.w /= fr;
+                float4 var = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                for (int v = 0; v < kViewsMax; ++v) {
+                    if (v < p.R) {
+                        float d;
+                        d = s[v].x - mean.x; var.x = fmaf(d, d, var.x);
+                        d = s[v].y - mean.y; var.y = fmaf(d, d, var.y);
+                        d = s[v].z - mean.z; var.z = fmaf(d, d, var.z);
+                        d = s[v].w - mean.w; var.w = fmaf(d, d, var.w);
+                    }
+                }
+                const float fu = (float)(p.R - 1);  // unbiased (torch.std default, refiner.py:237)
+                float4 sd;
+                sd.x = sqrtf(var.x / fu); sd.y = sqrtf(var.y / fu); sd.z = sqrtf(var.z / fu); sd.w = sqrtf(var.w / fu);
+                float* mrow = p.mean_in + orow * (2 * p.C);
+                __stcs(reinterpret_cast<float4*>(mrow + c), mean);
+                __stcs(reinterpret_cast<float4*>(mrow + p.C + c), qs);
+                __stcs(reinterpret_cast<float4*>(p.stdv + orow * p.C + c), sd);
             }
         }
-        const float fu = (float)(p.R - 1);  // unbiased (torch.std default, refiner.py:237)
-        float4 sd;
-        sd.x = sqrtf(var.x / fu); sd.y = sqrtf(var.y / fu); sd.z = sqrtf(var.z / fu); sd.w = sqrtf(var.w / fu);
-        const Taps qt = make_taps(p.que_Ks + (long long)qi * 9, qp, vx, vy, vz, p.fh, p.fw, p.img_h, p.img_w);
-        const float4 qs = sample4(p.que_feats + (long long)qi * fsz, qt, p.C, c);
-        float* mrow = p.mean_in + orow * (2 * p.C);
-        __stcs(reinterpret_cast<float4*>(mrow + c), mean);
-        __stcs(reinterpret_cast<float4*>(mrow + p.C + c), qs);
-        __stcs(reinterpret_cast<float4*>(p.stdv + orow * p.C + c), sd);
     }
 }
 
@@ -166,8 +189,9 @@ extern "C" int g6d_ref_volume_fill(const float* ref_feats, const float* que_feat
                 "g6d_ref_volume_fill: bad dims (2 <= R <= %d, C%%4 == 0, sn >= 2)", kMaxRefViews);
     VolParams p{ref_feats, que_feats, ref_Ks, ref_poses, que_Ks, que_poses, mean_in, stdv,
                 Q, R, fh, fw, C, sn, img_h, img_w};
-    const long long warps = (long long)Q * sn * sn * sn;
-    ref_volume_fill_kernel<<<ceil_div(warps, 8), 256, 0, as_stream(stream)>>>(p);
+    G6D_REQUIRE(R <= 7, "g6d_ref_volume_fill: at most 7 reference views (7 + query fill the 8 projection lanes x 4 voxels)");
+    const long long bricks = (long long)((sn + 1) / 2) * ((sn + 3) / 4) * ((sn + 7) / 8);
+    ref_volume_fill_kernel<<<(unsigned)(Q * bricks), 256, 0, as_stream(stream)>>>(p);
     G6D_CHECK_LAUNCH("g6d_ref_volume_fill");
     return G6D_OK;
 }

@@ -62,6 +62,85 @@ __global__ void __launch_bounds__(256) sel_corr_score_kernel(const float* __rest
 }
 
 // ------------------------------------------------------------------------------------------
+// S2, all pyramid levels in ONE streaming pass (what select_que_imgs uses): phase 1 computes
+// every per-location inner product t[row] for row = (level, slice, location) with a grid-stride
+// loop over rows -- the grid is sized to fill every SM with 64 resident warps regardless of S, and
+// each warp keeps two 2 KB rows (8 x 128-bit loads per lane) in flight; phase 2 (tiny, L2-resident)
+// reduces each (level, slice) to sum_p t*(t/max_p t).
+struct ScoreLevels {
+    const float* ref[3];   // [S, P_l, C]
+    const float* q[3];     // [P_l, C]
+    int P[3];
+    int S;
+    long long row_end[3];  // cumulative row counts: S*P_0, S*(P_0+P_1), S*(P_0+P_1+P_2)
+};
+
+template <int C>
+__device__ __forceinline__ float row_dot(const float4* __restrict__ rp, const float4* __restrict__ qp, int lane) {
+    constexpr int V = C / 128;
+    float4 rv[V];
+#pragma unroll
+    for (int i = 0; i < V; ++i) rv[i] = ldg_stream(rp + lane + 32 * i);
+    float t = 0.f;
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+        const float4 qv = __ldg(qp + lane + 32 * i);
+        t = fmaf(rv[i].x, qv.x, fmaf(rv[i].y, qv.y, fmaf(rv[i].z, qv.z, fmaf(rv[i].w, qv.w, t))));
+    }
+    return t;
+}
+
+template <int C>
+__global__ void __launch_bounds__(256) sel_corr_dots_kernel(const ScoreLevels L, float* __restrict__ t_out) {
+    const int lane = threadIdx.x & 31;
+    const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+    const long long rows = L.row_end[2];
+    auto locate = [&](long long row, const float4*& rp, const float4*& qp) {
+        // static selects (no dynamic indexing of the parameter struct -> no local-memory copy)
+        const bool l0 = row < L.row_end[0], l1 = row < L.row_end[1];
+        const long long local = row - (l0 ? 0 : (l1 ? L.row_end[0] : L.row_end[1]));      // = s*P_l + p
+        const int P = l0 ? L.P[0] : (l1 ? L.P[1] : L.P[2]);
+        const float* ref = l0 ? L.ref[0] : (l1 ? L.ref[1] : L.ref[2]);
+        const float* q = l0 ? L.q[0] : (l1 ? L.q[1] : L.q[2]);
+        const int p = (int)(local % P);
+        rp = reinterpret_cast<const float4*>(ref + local * C);
+        qp = reinterpret_cast<const float4*>(q + (long long)p * C);
+    };
+    for (long long row = warp * 2; row < rows; row += nwarps * 2) {
+        const float4 *r0, *q0, *r1, *q1;
+        locate(row, r0, q0);
+        const bool two = row + 1 < rows;
+        locate(two ? row + 1 : row, r1, q1);
+        float t0 = row_dot<C>(r0, q0, lane);
+        float t1 = row_dot<C>(r1, q1, lane);
+        t0 = warp_sum(t0);
+        t1 = warp_sum(t1);
+        if (lane == 0) {
+            t_out[row] = t0;
+            if (two) t_out[row + 1] = t1;
+        }
+    }
+}
+
+// one warp per (level, slice): score = sum_p t*(t/max_p t), reference operation order
+__global__ void sel_corr_finish_kernel(const ScoreLevels L, const float* __restrict__ t, float* __restrict__ score) {
+    const int lane = threadIdx.x & 31;
+    const int item = (int)(((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+    if (item >= 3 * L.S) return;
+    const int l = item / L.S, s = item % L.S;
+    const int P = l == 0 ? L.P[0] : (l == 1 ? L.P[1] : L.P[2]);
+    const float* tp = t + (l == 0 ? 0 : (l == 1 ? L.row_end[0] : L.row_end[1])) + (long long)s * P;
+    float m = -INFINITY;
+    for (int p = lane; p < P; p += 32) m = fmaxf(m, tp[p]);
+    m = warp_max(m);
+    float acc = 0.f;
+    for (int p = lane; p < P; p += 32) { const float v = tp[p]; acc += v * (v / m); }
+    acc = warp_sum(acc);
+    if (lane == 0) score[item] = acc;       // [3, S]
+}
+
+// ------------------------------------------------------------------------------------------
 // sum_s ref and sum_s ref^2 over the slice axis, doubles [P*C].  Load-time (once per object).
 __global__ void sel_ref_sums_kernel(const float* __restrict__ ref, int S, long long PC, int s_chunk,
                                     double* __restrict__ sum1, double* __restrict__ sum2) {
@@ -231,6 +310,29 @@ extern "C" int g6d_sel_corr_score(const float* ref, const float* q, int S, int P
     else if (C == 256) sel_corr_score_kernel<256><<<grid, 256, smem, st>>>(ref, q, S, P, score);
     else sel_corr_score_kernel<128><<<grid, 256, smem, st>>>(ref, q, S, P, score);
     G6D_CHECK_LAUNCH("g6d_sel_corr_score");
+    return G6D_OK;
+}
+
+extern "C" int g6d_sel_corr_score3(const float* ref0, const float* ref1, const float* ref2, const float* q0,
+                                   const float* q1, const float* q2, int S, int P0, int P1, int P2, int C, float* score,
+                                   float* ws, g6d_stream_t stream) {
+    G6D_REQUIRE(ref0 && ref1 && ref2 && q0 && q1 && q2 && score && ws && S > 0 && P0 > 0 && P1 > 0 && P2 > 0,
+                "g6d_sel_corr_score3: bad args");
+    G6D_REQUIRE(C == 512, "g6d_sel_corr_score3: C must be 512 (got %d)", C);
+    ScoreLevels L;
+    L.ref[0] = ref0; L.ref[1] = ref1; L.ref[2] = ref2; L.q[0] = q0; L.q[1] = q1; L.q[2] = q2;
+    L.P[0] = P0; L.P[1] = P1; L.P[2] = P2; L.S = S;
+    L.row_end[0] = (long long)S * P0; L.row_end[1] = L.row_end[0] + (long long)S * P1;
+    L.row_end[2] = L.row_end[1] + (long long)S * P2;
+    cudaStream_t st = as_stream(stream);
+    const long long pairs = (L.row_end[2] + 1) / 2;
+    long long grid = (pairs + 7) / 8;                    // 8 warps per CTA, one row pair per warp per trip
+    const long long full = 8ll * kNumSMs;                // 8 CTAs x 256 threads = 64 warps per SM
+    if (grid > full) grid = full;
+    sel_corr_dots_kernel<512><<<(unsigned)grid, 256, 0, st>>>(L, ws);
+    G6D_CHECK_LAUNCH("g6d_sel_corr_score3(dots)");
+    sel_corr_finish_kernel<<<ceil_div(3ll * S * 32, 256), 256, 0, st>>>(L, ws, score);
+    G6D_CHECK_LAUNCH("g6d_sel_corr_score3(finish)");
     return G6D_OK;
 }
 

@@ -23,6 +23,7 @@ class Gen6DEstimator:
         'detector': None,
         'refiner': None,
         'refine_iter': 3,
+        'host_threads': None,     # OpenCV / torch-CPU threads for the host geometry (None: min(8, usable CPUs))
     }
 
     def __init__(self, cfg, modules=None):
@@ -31,6 +32,7 @@ class Gen6DEstimator:
         synthetic checkpoints); otherwise they are loaded like estimator.py:117-125 does."""
         self.cfg = {**self.default_cfg, **cfg}
         self.ref_info = {}
+        G.configure_host_threads(self.cfg['host_threads'])
         if modules is not None:
             self.detector, self.selector = modules['detector'], modules['selector']
             self.refiner = modules.get('refiner')

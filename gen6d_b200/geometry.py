@@ -14,6 +14,31 @@ import cv2
 import numpy as np
 
 
+def usable_cpus():
+    """CPUs this process may really use: affinity mask capped by the cgroup quota."""
+    import os
+    n = len(os.sched_getaffinity(0)) if hasattr(os, 'sched_getaffinity') else (os.cpu_count() or 1)
+    try:
+        quota, period = open('/sys/fs/cgroup/cpu.max').read().split()
+        if quota != 'max':
+            n = min(n, max(1, int(float(quota) / float(period))))
+    except Exception:
+        pass
+    return max(1, n)
+
+
+def configure_host_threads(n=None):
+    """The per-frame host work is a handful of 128x128 warps, 3x3 linear algebra and sub-megabyte
+    staging copies.  OpenCV / OpenMP pools sized for every visible core (128 on the GPU hosts, with
+    a 16-CPU quota) make each of those calls slower by an order of magnitude, so the estimator caps
+    them (default: min(8, usable CPUs))."""
+    import torch
+    n = n or min(8, usable_cpus())
+    cv2.setNumThreads(n)
+    torch.set_num_threads(n)
+    return n
+
+
 # ------------------------------------------------------------------------------------------ poses
 def pose_inverse(pose):
     Rt = pose[:, :3].T

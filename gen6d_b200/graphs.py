@@ -11,6 +11,10 @@ import os
 
 import torch
 
+from . import _lib
+
+REPLAYED_KERNELS = [0]   # kernels launched through graph replays (the C-ABI launch counter only sees eager calls)
+
 
 def graphs_enabled():
     return os.environ.get('G6D_GRAPHS', '1') != '0'
@@ -29,13 +33,16 @@ class CapturedStage:
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
         self.graph = torch.cuda.CUDAGraph()
+        before = _lib.launch_count()
         with torch.cuda.graph(self.graph), torch.no_grad():
             self.static_out = fn(*self.static_in)
+        self.kernels = _lib.launch_count() - before     # kernel nodes captured (our C-ABI launches)
 
     def __call__(self, *inputs):
         for s, t in zip(self.static_in, inputs):
             s.copy_(t, non_blocking=True)
         self.graph.replay()
+        REPLAYED_KERNELS[0] += self.kernels
         return self.static_out
 
 

@@ -169,11 +169,11 @@ class ViewpointSelector(PackedModule):
         dev = self.device
         cat_buf = torch.empty(S, 4, 4, 768, device=dev, dtype=torch.float32)
         feats = torch.zeros(S, FEAT_PAD, device=dev, dtype=torch.float32)
-        scores = torch.empty(3, S, device=dev, dtype=torch.float32)
+        scores = ops.sel_corr_score3([r.reshape(S, -1, r.shape[-1]) for r in self.ref_feats_cache],
+                                     [q.reshape(-1, q.shape[-1]) for q in q_feats])
         for l, (q, ref, (s1, s2)) in enumerate(zip(q_feats, self.ref_feats_cache, self.ref_sums)):
             h, w, c = q.shape
             q2 = q.reshape(h * w, c)
-            ops.sel_corr_score(ref.reshape(S, h * w, c), q2, out=scores[l])
             scale, shift = ops.sel_corr_prologue(q2, s1, s2, S_total, IN_EPS)
             self._tower(l, ref, scale, shift, cat_buf, S)
         # corr_feats_conv (selector.py:71-77): 1x1 768->512, IN, ReLU, 1x1 512->512, AvgPool(4,4).

@@ -349,6 +349,17 @@ def sel_corr_score(ref, q, out=None):
     return out
 
 
+def sel_corr_score3(refs, qs):
+    """refs: 3 x [S, P_l, C]; qs: 3 x [P_l, C] -> score [3, S] in one streaming pass."""
+    S, Cc = refs[0].shape[0], refs[0].shape[2]
+    Ps = [r.shape[1] for r in refs]
+    out = torch.empty(3, S, device=refs[0].device, dtype=torch.float32)
+    ws = torch.empty(S * sum(Ps), device=refs[0].device, dtype=torch.float32)
+    _call('g6d_sel_corr_score3', _p(refs[0]), _p(refs[1]), _p(refs[2]), _p(qs[0]), _p(qs[1]), _p(qs[2]), S, Ps[0], Ps[1],
+          Ps[2], Cc, _p(out), _p(ws), _stream(), work=4.0 * (S * sum(Ps) * Cc + sum(Ps) * Cc + 3 * S))
+    return out
+
+
 def sel_vp_norm(score, feats, coff, eps=1e-5):
     Ln, n = score.shape
     _call('g6d_sel_vp_norm', _p(score), Ln, n, eps, _p(feats), feats.shape[-1], coff, _stream())

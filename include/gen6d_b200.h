@@ -192,6 +192,11 @@ int g6d_sel_corr_prologue(const float* q, const double* sum1, const double* sum2
 /* The rotated-similarity score, selector.py:183-186,192-194: s[p] = sum_c q[p,c]*ref[s,p,c];
  * score[s] = sum_p s[p]^2 / max_p s[p].  ref [S, P, C] is streamed once from HBM. */
 int g6d_sel_corr_score(const float* ref, const float* q, int S, int P, int C, float* score, g6d_stream_t stream);
+/* The same score for the three pyramid levels in one streaming pass (what select_que_imgs uses):
+ * score [3, S]; ws: S*(P0+P1+P2) floats (per-location inner products, L2-resident). */
+int g6d_sel_corr_score3(const float* ref0, const float* ref1, const float* ref2, const float* q0, const float* q1,
+                        const float* q2, int S, int P0, int P1, int P2, int C, float* score, float* ws,
+                        g6d_stream_t stream);
 /* vp_norm (InstanceNorm2d(3), selector.py:78,201): normalise each of the L score rows [L, n]
  * (biased var, eps) and scatter into feats[n, cstride] at channel coff + l. */
 int g6d_sel_vp_norm(const float* score, int L, int n, float eps, float* feats, int cstride, int coff,

@@ -144,6 +144,17 @@ def test_sel_corr_score_and_prologue(ops):
     close(scale, q * rstd[None], rtol=1e-4, atol=1e-6)
 
 
+def test_sel_corr_score3_matches_per_level(ops):
+    S = 10
+    refs = [F.normalize(torch.rand(S, P, 512, generator=g(30 + i)), dim=2) for i, P in enumerate((256, 64, 16))]
+    qs = [F.normalize(torch.rand(P, 512, generator=g(40 + i)), dim=1) for i, P in enumerate((256, 64, 16))]
+    got = ops.sel_corr_score3([r.cuda() for r in refs], [q.cuda() for q in qs])
+    for l in range(3):
+        s = torch.einsum('pc,spc->sp', qs[l], refs[l])
+        want = torch.sum(s * (s / s.max(1, keepdim=True)[0]), 1)
+        close(got[l], want, rtol=1e-5, atol=1e-6)
+
+
 def test_attention_layernorm(ops):
     n, Cc, heads = 24, 512, 8
     q, k, v = [torch.randn(n, Cc, generator=g(19 + i)) for i in range(3)]
