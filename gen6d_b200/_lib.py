@@ -51,6 +51,7 @@ _SIGNATURES = {
     'g6d_pack_conv_weight': [P, P, I, I, I, I, P, P],
     'g6d_conv_tc_supported': [C.POINTER(ConvDesc)],
     'g6d_conv_tc_debug': [C.POINTER(C.c_int)],
+    'g6d_debug_umma_shift': [P, I, I, P],
     'g6d_conv_tc_workspace_bytes': [C.POINTER(ConvDesc)],
     'g6d_conv_tc': [C.POINTER(ConvDesc), P, P, P, I, P, P, P, P, P, P],
     'g6d_pack_conv_weight_tc': [P, P, P, I, I, I, I, I, P, P],

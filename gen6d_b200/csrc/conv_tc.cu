@@ -21,9 +21,9 @@
 //              This warp also owns the TMEM allocation.
 // Small-M / huge-K problems are split along K over blockIdx.z into a workspace (same
 // deterministic reduce kernel as the FFMA path).
-#include <cuda.h>
+#include <stdlib.h>
 
-#include "common.cuh"
+#include "tc_common.cuh"
 
 namespace g6d {
 
@@ -41,102 +41,6 @@ struct ConvTcP {
     int M, K, kblocks, splits, kb_per_split;
 };
 
-// ------------------------------------------------------------------------------------------ PTX
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
-    uint32_t ok;
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.b32 %0, 1, 0, p;\n\t}"
-        : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
-    return ok != 0;
-}
-// Bounded wait: a protocol bug must never hang the GPU.  On timeout (~0.25 s) the waiter records
-// who was waiting on what in g_tc_timeout (read back with g6d_conv_tc_debug) and every wait in the
-// grid falls through, so the kernel terminates (with garbage output) instead of spinning.
-__device__ int g_tc_timeout[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int who = 0, int iter = 0) {
-    if (mbar_try_wait(bar, parity)) return;
-    const long long t0 = clock64();
-    while (!mbar_try_wait(bar, parity)) {
-        if (*(volatile int*)&g_tc_timeout[0] != 0) return;
-        if (clock64() - t0 > 500000000ll) {
-            if (atomicCAS(&g_tc_timeout[0], 0, 1) == 0) {
-                g_tc_timeout[1] = who; g_tc_timeout[2] = iter; g_tc_timeout[3] = (int)parity;
-                g_tc_timeout[4] = (int)blockIdx.x; g_tc_timeout[5] = (int)blockIdx.y; g_tc_timeout[6] = (int)blockIdx.z;
-                g_tc_timeout[7] = (int)threadIdx.x;
-            }
-            return;
-        }
-    }
-}
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-
-__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
-    asm volatile(
-        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-        ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1) : "memory");
-}
-
-// K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start
-// address >> 4 in bits [0,14); LBO (ignored for swizzled K-major) = 1 in [16,30); SBO = 1024 B
-// (8 rows x 128 B) >> 4 in [32,46); descriptor version 1 in [46,48); layout SWIZZLE_128B (=2)
-// in [61,64).  The tile base must be 1024-byte aligned (base_offset = 0).
-__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
-    uint64_t d = 0;
-    d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
-    d |= (uint64_t)1 << 16;
-    d |= (uint64_t)(1024 >> 4) << 32;
-    d |= (uint64_t)1 << 46;
-    d |= (uint64_t)2 << 61;
-    return d;
-}
-
-// cute::UMMA::InstrDescriptor for kind::tf32, fp32 accumulate, both operands K-major:
-// c_format F32 (1) at [4,6); a_format/b_format TF32 (2) at [7,10)/[10,13); n_dim = N>>3 at
-// [17,23); m_dim = M>>4 at [24,29).
-__device__ __forceinline__ uint32_t umma_idesc_tf32(int M, int N) {
-    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
-}
-
-__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
-                                          uint32_t accumulate) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
-        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-
-__device__ __forceinline__ float to_tf32(float v) {
-    uint32_t r;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
-    return __uint_as_float(r);
-}
-
-__device__ __forceinline__ float tc_act(float v, int act) {
-    if (act == G6D_ACT_RELU) return fmaxf(v, 0.f);
-    if (act == G6D_ACT_LEAKY01) return v > 0.f ? v : 0.1f * v;
-    return v;
-}
 
 template <int BN> struct TcCfg {
     static constexpr int A_BYTES = TC_BM * 128;            // one A tile (hi or lo)
@@ -565,6 +469,334 @@ __global__ void pack_conv_weight_tc_kernel(const float* __restrict__ w, float* _
     lo[i] = to_tf32(v - h);
 }
 
+// ==========================================================================================
+// conv_tcflat_kernel: stride-1 convolutions with A-operand reuse across taps.
+//
+// The output positions of one image plane are enumerated over the PADDED width Wp = W + 2*pw:
+// f = y*Wp + x.  Tap (ky,kx) of output f reads padded-input position f + ky*Wp + kx, so for a
+// tile of 128 consecutive f the A operand of EVERY tap is a window of 128 consecutive rows of
+// one shared-memory buffer holding padded-input positions [f0, f0 + 127 + (kh-1)*Wp + kw-1]:
+// the tap is selected by the UMMA descriptor's start address (+shift*128 B; the 128B swizzle is a
+// function of the absolute smem address, verified by g6d_debug_umma_shift).  The producers
+// therefore gather (and prologue-transform, and hi/lo split) each input element ONCE per channel
+// block instead of once per tap: 9x less producer work / L2 traffic for 3x3 ("FLAT" mode).  When
+// the halo (kh-1)*Wp does not fit in shared memory (wide images, 15x15 correlation kernels) the
+// buffer holds one kernel row at a time ("ROW" mode: kw-fold reuse).  Columns x >= Wo of the
+// padded enumeration are computed and dropped.  B tiles stream by TMA per (channel block, tap).
+struct ConvFlatP {
+    const float* x; const float* bias; const float* ps; const float* pb; float* y; float* ws;
+    int B, D, H, W, Cin, ics, ico, Cout, kd, kh, kw, pd, ph, pw, Do, Ho, Wo, ocs, oco, pro, act;
+    long long group_rows;
+    int Wp, tiles_per_plane, mode, nseg, taps_per_seg, seg_rows, rows_pad, ntab, cblocks;
+    int a_stages, b_stages, splits, cb_per_split, M;
+};
+
+template <int BN>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+conv_tcflat_kernel(const ConvFlatP p, const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CUtensorMap map_lo) {
+    constexpr int NMAIN = TcCfg<BN>::NMAIN;
+    constexpr int TMEM_COLS = TcCfg<BN>::TMEM_COLS;
+    constexpr int B_BYTES = BN * 128;
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t* base_ptr = smem_raw + (base - smem_u32(smem_raw));
+    const int A_TILE = p.rows_pad * 128;                 // one of hi / lo
+    const uint32_t a_base = base;
+    const uint32_t b_base = base + p.a_stages * 2 * A_TILE;
+    const uint32_t bar_base = b_base + p.b_stages * 2 * B_BYTES;
+    auto a_hi = [&](int s) { return a_base + s * 2 * A_TILE; };
+    auto a_lo = [&](int s) { return a_base + s * 2 * A_TILE + A_TILE; };
+    auto b_hi = [&](int s) { return b_base + s * 2 * B_BYTES; };
+    auto b_lo = [&](int s) { return b_base + s * 2 * B_BYTES + B_BYTES; };
+    auto a_full = [&](int s) { return bar_base + 8 * s; };
+    auto a_empty = [&](int s) { return bar_base + 8 * (4 + s); };
+    auto b_full = [&](int s) { return bar_base + 8 * (8 + s); };
+    auto b_empty = [&](int s) { return bar_base + 8 * (12 + s); };
+    const uint32_t tmem_full = bar_base + 8 * 16;
+    const uint32_t bar_off = (bar_base - base);
+    volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(base_ptr + bar_off + 8 * 17);
+    int* rowtab = reinterpret_cast<int*>(base_ptr + bar_off + 256);   // [ntab][seg_rows]
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    int tile = blockIdx.x;
+    const int t_in_plane = tile % p.tiles_per_plane; tile /= p.tiles_per_plane;
+    const int zo = tile % p.Do;
+    const int b = tile / p.Do;
+    const int f0 = t_in_plane * TC_BM;
+    const int n_base = blockIdx.y * BN;
+    const int split = blockIdx.z;
+    const int cb_begin = split * p.cb_per_split;
+    const int cb_end = min(p.cblocks, cb_begin + p.cb_per_split);
+    const int nunits = (cb_end - cb_begin) * p.nseg;
+
+    // ---- setup: row tables (element offset of each gathered row inside its image plane, -1 = zero)
+    for (int e = threadIdx.x; e < p.ntab * p.seg_rows; e += blockDim.x) {
+        const int tb = e / p.seg_rows, i = e % p.seg_rows;
+        const int g = f0 + (p.mode == 1 ? tb * p.Wp : 0) + i;     // padded-input flat position
+        const int yy = g / p.Wp - p.ph, xx = g % p.Wp - p.pw;
+        rowtab[e] = ((unsigned)yy < (unsigned)p.H && (unsigned)xx < (unsigned)p.W) ? yy * p.W + xx : -1;
+    }
+    if (warp == TC_PRODUCER_WARPS && lane == 0) {
+        for (int s = 0; s < 4; ++s) {
+            mbar_init(a_full(s), TC_PRODUCER_WARPS);
+            mbar_init(a_empty(s), 1);
+            mbar_init(b_full(s), 1);
+            mbar_init(b_empty(s), 1);
+        }
+        mbar_init(tmem_full, 1);
+        fence_barrier_init();
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_hi) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_lo) : "memory");
+    }
+    if (warp == TC_PRODUCER_WARPS + 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+                     ::"r"(smem_u32((const void*)tmem_slot)), "n"(TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_acc = *tmem_slot;
+
+    if (warp < TC_PRODUCER_WARPS) {
+        // =============================== A producers ===============================
+        const int chunk = threadIdx.x & 7;
+        const int r0 = threadIdx.x >> 3;                        // rows r0 + 32*j
+        const long long plane = (long long)p.H * p.W;
+        const long long gi = (long long)b / p.group_rows;
+        for (int u = 0; u < nunits; ++u) {
+            const int cb = cb_begin + u / p.nseg, seg = u % p.nseg;
+            const int s = u % p.a_stages;
+            const uint32_t n_use = u / p.a_stages;
+            // FLAT: seg = kz, table 0.  ROW: seg = kz*kh + ky, table ky.
+            const int kz = p.mode == 1 ? seg / p.kh : seg;
+            const int tb = p.mode == 1 ? seg % p.kh : 0;
+            const int zz = zo + kz - p.pd;
+            const bool zok = (unsigned)zz < (unsigned)p.D;
+            const float* xplane = p.x + ((long long)b * p.D + (zok ? zz : 0)) * plane * p.ics + p.ico + cb * TC_BK + chunk * 4;
+            const int* tab = rowtab + tb * p.seg_rows;
+            const int c = cb * TC_BK + chunk * 4;
+            mbar_wait(a_empty(s), (n_use & 1) ^ 1, 1, u);
+            for (int rbase = 0; rbase < p.seg_rows; rbase += 128) {        // 4 rows per thread per trip
+                float4 v[4]; int off[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int r = rbase + r0 + 32 * j;
+                    off[j] = (r < p.seg_rows && zok) ? tab[r] : -1;
+                    v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (off[j] >= 0) v[j] = __ldg(reinterpret_cast<const float4*>(xplane + (long long)off[j] * p.ics));
+                }
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int r = rbase + r0 + 32 * j;
+                    if (r >= p.rows_pad) continue;
+                    float4 x4 = v[j];
+                    if (p.pro != G6D_PRO_NONE && off[j] >= 0) {
+                        float4 sc, sh;
+                        if (p.pro == G6D_PRO_CORR) {
+                            const long long sp = (long long)zz * plane + off[j];
+                            sc = __ldg(reinterpret_cast<const float4*>(p.ps + sp * p.Cin + c));
+                            sh = __ldg(reinterpret_cast<const float4*>(p.pb + c));
+                        } else {
+                            sc = __ldg(reinterpret_cast<const float4*>(p.ps + gi * p.Cin + c));
+                            sh = __ldg(reinterpret_cast<const float4*>(p.pb + gi * p.Cin + c));
+                        }
+                        x4.x = fmaf(x4.x, sc.x, sh.x); x4.y = fmaf(x4.y, sc.y, sh.y);
+                        x4.z = fmaf(x4.z, sc.z, sh.z); x4.w = fmaf(x4.w, sc.w, sh.w);
+                        if (p.pro == G6D_PRO_AFFINE_RELU) {
+                            x4.x = fmaxf(x4.x, 0.f); x4.y = fmaxf(x4.y, 0.f); x4.z = fmaxf(x4.z, 0.f); x4.w = fmaxf(x4.w, 0.f);
+                        }
+                    }
+                    float4 hi, lo;
+                    hi.x = __uint_as_float((__float_as_uint(x4.x) + 0x1000u) & 0xFFFFE000u);
+                    hi.y = __uint_as_float((__float_as_uint(x4.y) + 0x1000u) & 0xFFFFE000u);
+                    hi.z = __uint_as_float((__float_as_uint(x4.z) + 0x1000u) & 0xFFFFE000u);
+                    hi.w = __uint_as_float((__float_as_uint(x4.w) + 0x1000u) & 0xFFFFE000u);
+                    lo.x = x4.x - hi.x; lo.y = x4.y - hi.y; lo.z = x4.z - hi.z; lo.w = x4.w - hi.w;
+                    const uint32_t so = r * 128 + ((chunk ^ (r & 7)) << 4);
+                    asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(a_hi(s) + so), "f"(hi.x), "f"(hi.y), "f"(hi.z), "f"(hi.w) : "memory");
+                    asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(a_lo(s) + so), "f"(lo.x), "f"(lo.y), "f"(lo.z), "f"(lo.w) : "memory");
+                }
+            }
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(a_full(s));
+        }
+
+        // =============================== epilogue ===============================
+        mbar_wait(tmem_full, 0, 2, nunits);
+        tc_fence_after();
+        const int quad = warp & 3;
+        const int row = quad * 32 + lane;
+        const int f = f0 + row;
+        const int yo = f / p.Wp, xo = f % p.Wp;
+        const bool valid = yo < p.Ho && xo < p.Wo;
+        const long long m = (((long long)b * p.Do + zo) * p.Ho + yo) * p.Wo + xo;
+        constexpr int HALF = BN / 2;
+        const int col0 = (warp >> 2) * HALF;
+        const bool partial = p.splits > 1;
+        const int total_mm = nunits * p.taps_per_seg;
+        const int n_acc = total_mm < NMAIN ? total_mm : NMAIN;
+#pragma unroll
+        for (int cc = 0; cc < HALF; cc += 16) {
+            float accv[16];
+            const uint32_t taddr = tmem_acc + ((uint32_t)(quad * 32) << 16) + (uint32_t)(col0 + cc);
+#pragma unroll
+            for (int a = 0; a <= NMAIN; ++a) {
+                const bool used = a == NMAIN || a < n_acc;
+                uint32_t r[16];
+                if (used) {
+                    asm volatile(
+                        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+                        : "r"(taddr + (uint32_t)(a * BN)));
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) accv[j] = a == 0 ? __uint_as_float(r[j]) : accv[j] + __uint_as_float(r[j]);
+                }
+            }
+            if (valid) {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    const int n = n_base + col0 + cc + j;
+                    if (n < p.Cout) {
+                        float v = accv[j];
+                        if (partial) {
+                            p.ws[((long long)split * p.M + m) * p.Cout + n] = v;
+                        } else {
+                            if (p.bias) v += __ldg(p.bias + n);
+                            p.y[m * p.ocs + p.oco + n] = tc_act(v, p.act);
+                        }
+                    }
+                }
+            }
+        }
+        tc_fence_before();
+    } else if (warp == TC_PRODUCER_WARPS) {
+        // =============================== B producer (TMA) ===============================
+        if (lane == 0) {
+            int bi = 0;
+            for (int u = 0; u < nunits; ++u) {
+                const int cb = cb_begin + u / p.nseg, seg = u % p.nseg;
+                for (int t = 0; t < p.taps_per_seg; ++t, ++bi) {
+                    const int s = bi % p.b_stages;
+                    const uint32_t n_use = bi / p.b_stages;
+                    mbar_wait(b_empty(s), (n_use & 1) ^ 1, 3, bi);
+                    mbar_expect_tx(b_full(s), 2 * B_BYTES);
+                    const int k = (seg * p.taps_per_seg + t) * p.Cin + cb * TC_BK;
+                    tma_load_2d(b_hi(s), &map_hi, b_full(s), k, n_base);
+                    tma_load_2d(b_lo(s), &map_lo, b_full(s), k, n_base);
+                }
+            }
+        }
+    } else {
+        // =============================== MMA issuer ===============================
+        if (lane == 0) {
+            const uint32_t idesc = umma_idesc_tf32(TC_BM, BN);
+            int bi = 0;
+            for (int u = 0; u < nunits; ++u) {
+                const int sa = u % p.a_stages;
+                mbar_wait(a_full(sa), (u / p.a_stages) & 1, 4, u);
+                tc_fence_after();
+                for (int t = 0; t < p.taps_per_seg; ++t, ++bi) {
+                    const int sb = bi % p.b_stages;
+                    mbar_wait(b_full(sb), (bi / p.b_stages) & 1, 5, bi);
+                    tc_fence_after();
+                    const int shift = p.mode == 1 ? t : (t / p.kw) * p.Wp + (t % p.kw);     // rows
+                    const uint64_t dah = umma_desc_sw128(a_hi(sa) + shift * 128), dal = umma_desc_sw128(a_lo(sa) + shift * 128);
+                    const uint64_t dbh = umma_desc_sw128(b_hi(sb)), dbl = umma_desc_sw128(b_lo(sb));
+                    const uint32_t main_acc = tmem_acc + (uint32_t)((bi % NMAIN) * BN);
+                    const uint32_t cross_acc = tmem_acc + (uint32_t)(NMAIN * BN);
+#pragma unroll
+                    for (int ks = 0; ks < TC_BK / 8; ++ks) {
+                        const uint64_t adv = (uint64_t)((ks * 32) >> 4);
+                        umma_tf32(cross_acc, dal + adv, dbh + adv, idesc, (bi > 0 || ks > 0) ? 1u : 0u);
+                        umma_tf32(cross_acc, dah + adv, dbl + adv, idesc, 1u);
+                        umma_tf32(main_acc, dah + adv, dbh + adv, idesc, (bi >= NMAIN || ks > 0) ? 1u : 0u);
+                    }
+                    umma_commit(b_empty(sb));
+                }
+                umma_commit(a_empty(sa));
+            }
+            umma_commit(tmem_full);
+        }
+    }
+    __syncthreads();
+    if (warp == TC_PRODUCER_WARPS + 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_acc), "n"(TMEM_COLS) : "memory");
+    }
+}
+
+static int fill_flat_params(const g6d_conv_desc* d, ConvFlatP& p, int* smem_bytes) {
+    if (!d || d->stride != 1 || (d->Cin % TC_BK) != 0 || d->Cout < 16 || (d->in_cstride & 3) || (d->in_coff & 3)) return -1;
+    const int Do = d->D + 2 * d->pd - d->kd + 1, Ho = d->H + 2 * d->ph - d->kh + 1, Wo = d->W + 2 * d->pw - d->kw + 1;
+    if (Do != d->Do || Ho != d->Ho || Wo != d->Wo || Do < 1 || Ho < 1 || Wo < 1) return -1;
+    if (d->kd * d->kh * d->kw == 1) return -1;                        // 1x1: nothing to reuse, old kernel
+    const int bn = d->Cout > 64 ? 128 : (d->Cout > 32 ? 64 : 32);
+    const int Wp = d->W + 2 * d->pw;
+    const int flat_rows = TC_BM + (d->kh - 1) * Wp + d->kw - 1;
+    const int row_rows = TC_BM + d->kw - 1;
+    const int budget = 220 * 1024;
+    const int b_stage = 2 * bn * 128;
+    // tiles never span image planes: small planes (selector 4x4 / 8x8 maps) would leave most of a
+    // 128-row tile empty -> keep those on the batch-flattened kernel
+    {
+        const long long tiles = ((long long)Ho * Wp + TC_BM - 1) / TC_BM;
+        if ((long long)Ho * Wo * 100 < tiles * TC_BM * 60) return -1;
+    }
+    auto a_stage = [](int rows) { return 2 * ((rows + 7) / 8 * 8) * 128; };
+    int mode, rows, ntab;
+    // FLAT when two A stages of the full halo + >= 3 B stages fit
+    if (2 * a_stage(flat_rows) + 3 * b_stage + 4 * flat_rows + 2048 <= budget) { mode = 0; rows = flat_rows; ntab = 1; }
+    else if (d->kw > 1) { mode = 1; rows = row_rows; ntab = d->kh; }
+    else return -1;
+    p.B = d->B; p.D = d->D; p.H = d->H; p.W = d->W; p.Cin = d->Cin; p.ics = d->in_cstride; p.ico = d->in_coff;
+    p.Cout = d->Cout; p.kd = d->kd; p.kh = d->kh; p.kw = d->kw; p.pd = d->pd; p.ph = d->ph; p.pw = d->pw;
+    p.Do = Do; p.Ho = Ho; p.Wo = Wo; p.ocs = d->out_cstride; p.oco = d->out_coff; p.pro = d->prologue; p.act = d->act;
+    p.group_rows = d->group_rows > 0 ? d->group_rows : 1;
+    p.Wp = Wp; p.tiles_per_plane = (Ho * Wp + TC_BM - 1) / TC_BM; p.mode = mode;
+    p.nseg = mode == 0 ? d->kd : d->kd * d->kh; p.taps_per_seg = mode == 0 ? d->kh * d->kw : d->kw;
+    p.seg_rows = rows; p.rows_pad = (rows + 7) / 8 * 8; p.ntab = ntab; p.cblocks = d->Cin / TC_BK;
+    const long long M = (long long)d->B * Do * Ho * Wo;
+    if (M >= (1ll << 31)) return -1;
+    p.M = (int)M;
+    const int tab_bytes = 4 * ntab * rows;
+    int a_st = 2, b_st = 3;
+    int used = a_st * a_stage(rows) + b_st * b_stage + tab_bytes + 2048;
+    while (b_st < 4 && used + b_stage <= budget) { ++b_st; used += b_stage; }
+    while (a_st < 4 && used + a_stage(rows) <= budget) { ++a_st; used += a_stage(rows); }
+    if (used > budget) return -1;
+    p.a_stages = a_st; p.b_stages = b_st;
+    *smem_bytes = a_st * a_stage(rows) + b_st * b_stage + 256 + tab_bytes + 1024 + 64;
+    // split over channel blocks when the tile grid cannot fill the machine, or to bound accumulate chains
+    const long long ctas = (long long)d->B * Do * p.tiles_per_plane * ((d->Cout + bn - 1) / bn);
+    const long long kblocks = (long long)p.cblocks * d->kd * d->kh * d->kw;
+    int splits = 1;
+    if (ctas < kNumSMs && p.cblocks >= 2) splits = (int)((kNumSMs + ctas - 1) / ctas);
+    if (kblocks > 256) { const int ms = (int)((kblocks + TC_MAX_KB_PER_SPLIT - 1) / TC_MAX_KB_PER_SPLIT); splits = splits < ms ? ms : splits; }
+    splits = splits > p.cblocks ? p.cblocks : splits;
+    splits = splits < 1 ? 1 : splits;
+    p.cb_per_split = (p.cblocks + splits - 1) / splits;
+    p.splits = (p.cblocks + p.cb_per_split - 1) / p.cb_per_split;
+    return 0;
+}
+
+template <int BN>
+static int launch_flat(const ConvFlatP& p, int smem, const CUtensorMap& mh, const CUtensorMap& ml, cudaStream_t st) {
+    static int configured = 0;
+    if (configured < smem) {
+        cudaError_t e = cudaFuncSetAttribute(conv_tcflat_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (e != cudaSuccess) { set_error("g6d_conv_tc(flat): cannot opt in to shared memory: %s", cudaGetErrorString(e)); return G6D_ECUDA; }
+        configured = 227 * 1024;
+    }
+    dim3 grid((unsigned)((long long)p.B * p.Do * p.tiles_per_plane), ceil_div(p.Cout, BN), p.splits);
+    conv_tcflat_kernel<BN><<<grid, TC_THREADS, smem, st>>>(p, mh, ml);
+    G6D_CHECK_LAUNCH("g6d_conv_tc(flat)");
+    return G6D_OK;
+}
+
 }  // namespace g6d
 
 using namespace g6d;
@@ -588,7 +820,18 @@ extern "C" int g6d_conv_tc_supported(const g6d_conv_desc* d) {
     return (d->Cin % TC_BK) == 0 && d->Cout >= 16 && (d->in_cstride & 3) == 0 && (d->in_coff & 3) == 0 ? 1 : 0;
 }
 
+static bool flat_disabled() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("G6D_CONV_FLAT"); v = (e && e[0] == '0') ? 1 : 0; }
+    return v == 1;
+}
+
 extern "C" long long g6d_conv_tc_workspace_bytes(const g6d_conv_desc* desc) {
+    {
+        ConvFlatP fp{}; int smem = 0;
+        if (!flat_disabled() && fill_flat_params(desc, fp, &smem) == 0)
+            return fp.splits > 1 ? (long long)fp.splits * fp.M * fp.Cout * (long long)sizeof(float) : 0;
+    }
     ConvTcP p{};
     if (fill_tc_params(desc, p) != G6D_OK) return -1;
     return p.splits > 1 ? (long long)p.splits * p.M * p.Cout * (long long)sizeof(float) : 0;
@@ -597,6 +840,33 @@ extern "C" long long g6d_conv_tc_workspace_bytes(const g6d_conv_desc* desc) {
 extern "C" int g6d_conv_tc(const g6d_conv_desc* desc, const float* x, const float* w_hi, const float* w_lo,
                            int w_rows, const float* bias, const float* pro_scale, const float* pro_shift, float* y,
                            void* ws, g6d_stream_t stream) {
+    {   // stride-1 multi-tap convolutions: A-reuse kernel
+        ConvFlatP fp{}; int smem = 0;
+        if (!flat_disabled() && fill_flat_params(desc, fp, &smem) == 0) {
+            G6D_REQUIRE(x && w_hi && w_lo && y, "g6d_conv_tc: null tensor pointer");
+            G6D_REQUIRE(w_rows >= fp.Cout, "g6d_conv_tc: weight rows (%d) < Cout (%d)", w_rows, fp.Cout);
+            if (fp.pro != G6D_PRO_NONE) G6D_REQUIRE(pro_scale && pro_shift, "g6d_conv_tc: prologue operands missing");
+            if (fp.splits > 1) G6D_REQUIRE(ws != nullptr, "g6d_conv_tc: split workspace required (%d splits)", fp.splits);
+            fp.x = x; fp.bias = bias; fp.ps = pro_scale; fp.pb = pro_shift; fp.y = y; fp.ws = (float*)ws;
+            const int bn = tc_block_n(fp.Cout);
+            const int K = fp.kd * fp.kh * fp.kw * fp.Cin;
+            CUtensorMap mh, ml;
+            int rc2;
+            if ((rc2 = make_weight_map(&mh, w_hi, w_rows, K, bn)) != G6D_OK) return rc2;
+            if ((rc2 = make_weight_map(&ml, w_lo, w_rows, K, bn)) != G6D_OK) return rc2;
+            cudaStream_t st = as_stream(stream);
+            if (bn == 128) rc2 = launch_flat<128>(fp, smem, mh, ml, st);
+            else if (bn == 64) rc2 = launch_flat<64>(fp, smem, mh, ml, st);
+            else rc2 = launch_flat<32>(fp, smem, mh, ml, st);
+            if (rc2 != G6D_OK) return rc2;
+            if (fp.splits > 1) {
+                const long long n = (long long)fp.M * fp.Cout;
+                conv_tc_reduce_kernel<<<ceil_div(n, 256), 256, 0, st>>>(fp.ws, bias, y, fp.M, fp.Cout, fp.splits, fp.ocs, fp.oco, fp.act);
+                G6D_CHECK_LAUNCH("g6d_conv_tc(flat reduce)");
+            }
+            return G6D_OK;
+        }
+    }
     ConvTcP p{};
     int rc = fill_tc_params(desc, p);
     if (rc != G6D_OK) return rc;
@@ -637,5 +907,76 @@ extern "C" int g6d_pack_conv_weight_tc(const float* w, float* out_hi, float* out
     pack_conv_weight_tc_kernel<<<ceil_div(total, 256), 256, 0, as_stream(stream)>>>(w, out_hi, out_lo, Cout, Cin, Cin_pad,
                                                                                     taps, rows_pad, cout_scale);
     G6D_CHECK_LAUNCH("g6d_pack_conv_weight_tc");
+    return G6D_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// Probe (debug/test only): does a K-major SWIZZLE_128B A operand tolerate a start address that is
+// shifted by `shift` rows (shift*128 B, not 1024-aligned) when the data was written with the
+// swizzle phase of its ABSOLUTE shared-memory row?  D[128 x 32] = A[shift .. shift+128) x B^T with
+// K = 32, A[r][k] = r + k/64 (exactly representable), B = 32x32 identity.  `mode` selects how the
+// descriptor's base_offset field is set: 0 -> 0, 1 -> (start_address >> 7) & 7.
+namespace g6d {
+__global__ void __launch_bounds__(128) umma_shift_probe_kernel(float* out, int shift, int mode) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t* bp = smem_raw + (base - smem_u32(smem_raw));
+    const uint32_t a_base = base;                 // 160 rows x 128 B
+    const uint32_t b_base = base + 160 * 128;     // 32 rows x 128 B (20480 is 1024-aligned)
+    const uint32_t bar = b_base + 32 * 128;
+    volatile uint32_t* slot = reinterpret_cast<volatile uint32_t*>(bp + 160 * 128 + 32 * 128 + 16);
+    const int t = threadIdx.x;
+    for (int r = t; r < 160; r += 128)
+        for (int c = 0; c < 8; ++c) {
+            float4 v = make_float4(r + (c * 4 + 0) / 64.f, r + (c * 4 + 1) / 64.f, r + (c * 4 + 2) / 64.f, r + (c * 4 + 3) / 64.f);
+            *reinterpret_cast<float4*>(bp + r * 128 + ((c ^ (r & 7)) << 4)) = v;
+        }
+    for (int r = t; r < 32; r += 128)
+        for (int c = 0; c < 8; ++c) {
+            float4 v = make_float4(r == c * 4 ? 1.f : 0.f, r == c * 4 + 1 ? 1.f : 0.f, r == c * 4 + 2 ? 1.f : 0.f, r == c * 4 + 3 ? 1.f : 0.f);
+            *reinterpret_cast<float4*>(bp + 160 * 128 + r * 128 + ((c ^ (r & 7)) << 4)) = v;
+        }
+    fence_proxy_async();
+    if (t == 0) { mbar_init(bar, 1); fence_barrier_init(); }
+    if (t < 32) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 32;" ::"r"(smem_u32((const void*)slot)) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *slot;
+    if (t == 0) {
+        const uint32_t start = a_base + shift * 128;
+        uint64_t da = umma_desc_sw128(start);
+        if (mode == 1) da |= (uint64_t)((start >> 7) & 7) << 49;
+        const uint64_t db = umma_desc_sw128(b_base);
+        const uint32_t idesc = umma_idesc_tf32(128, 32);
+        for (int ks = 0; ks < 4; ++ks) umma_tf32(tmem, da + (uint64_t)(ks * 2), db + (uint64_t)(ks * 2), idesc, ks > 0);
+        umma_commit(bar);
+    }
+    mbar_wait(bar, 0, 9, 0);
+    tc_fence_after();
+    const int warp = t >> 5, lane = t & 31;
+    for (int cc = 0; cc < 32; cc += 16) {
+        uint32_t r[16];
+        asm volatile(
+            "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+            : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+              "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+            : "r"(tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)cc));
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        for (int j = 0; j < 16; ++j) out[(warp * 32 + lane) * 32 + cc + j] = __uint_as_float(r[j]);
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (t < 32) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 32;" ::"r"(tmem) : "memory");
+}
+}  // namespace g6d
+
+extern "C" int g6d_debug_umma_shift(float* out, int shift, int mode, g6d_stream_t stream) {
+    G6D_REQUIRE(out && shift >= 0 && shift <= 31, "g6d_debug_umma_shift: bad args");
+    g6d::umma_shift_probe_kernel<<<1, 128, 160 * 128 + 32 * 128 + 1024 + 64, g6d::as_stream(stream)>>>(out, shift, mode);
+    G6D_CHECK_LAUNCH("g6d_debug_umma_shift");
     return G6D_OK;
 }

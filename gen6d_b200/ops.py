@@ -31,13 +31,15 @@ def _p(t, dtype=torch.float32):
 _PROFILE = None   # when enabled: {name: [(start_event, end_event, work), ...]}
 
 
-def _call(name, *args, work=None):
+def _call(name, *args, work=None, tag=None):
     if _PROFILE is not None and work is not None:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         _lib.check(getattr(_lib.lib(), name)(*args), name)
         e1.record()
         _PROFILE.setdefault(name, []).append((e0, e1, work))
+        if tag is not None:
+            _PROFILE.setdefault('#calls', []).append((e0, e1, work, name, tag))
         return
     _lib.check(getattr(_lib.lib(), name)(*args), name)
 
@@ -54,8 +56,11 @@ def collect_profile(prof):
     global _PROFILE
     torch.cuda.synchronize()
     _PROFILE = None
-    return {k: {'ms': sum(a.elapsed_time(b) for a, b, _ in v), 'work': float(sum(w for _, _, w in v)), 'n': len(v)}
-            for k, v in prof.items()}
+    out = {k: {'ms': sum(r[0].elapsed_time(r[1]) for r in v), 'work': float(sum(r[2] for r in v)), 'n': len(v)}
+           for k, v in prof.items() if k != '#calls'}
+    if '#calls' in prof:
+        out['#calls'] = [(r[0].elapsed_time(r[1]), r[2], r[3], r[4]) for r in prof['#calls']]
+    return out
 
 
 def require_cuda():
@@ -273,7 +278,8 @@ def conv(x, pc, prologue=PRO_NONE, pro_scale=None, pro_shift=None, group_rows=1,
             _lib.check(-1, 'g6d_conv_tc_workspace_bytes')
         ws = torch.empty(nbytes // 4, device=x.device, dtype=torch.float32) if nbytes > 0 else None
         _call('g6d_conv_tc', C.byref(d), _p(x), _p(pc.w_hi), _p(pc.w_lo), pc.w_hi.shape[0], _p(pc.bias), _p(pro_scale),
-              _p(pro_shift), _p(out), _p(ws), _stream(), work=work)
+              _p(pro_shift), _p(out), _p(ws), _stream(), work=work,
+              tag=f'M={B * Do * Ho * Wo} N={pc.cout} K={kd * kh * kw * pc.cin} k={kd}x{kh}x{kw} s={s} pro={prologue}')
         return out
     nbytes = _lib.lib().g6d_conv_workspace_bytes(C.byref(d))
     if nbytes < 0:

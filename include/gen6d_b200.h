@@ -140,6 +140,8 @@ int g6d_pack_conv_weight(const float* w, float* out, int Cout, int Cin, int Cin_
  * g6d_split_tf32.  A tiles are gathered + transformed by producer warps, B tiles arrive by TMA,
  * accumulators live in TMEM. */
 int g6d_conv_tc_supported(const g6d_conv_desc* desc);
+/* debug probe: D[128x32] = A[shift..shift+128) x I for a row-shifted SWIZZLE_128B descriptor (mode: base_offset rule) */
+int g6d_debug_umma_shift(float* out, int shift, int mode, g6d_stream_t stream);
 /* debug: host_out8[0] != 0 if a pipeline wait inside g6d_conv_tc timed out (kernel bailed out); syncs */
 int g6d_conv_tc_debug(int* host_out8);
 long long g6d_conv_tc_workspace_bytes(const g6d_conv_desc* desc);
