@@ -250,6 +250,7 @@ def run_ours(args, rank, world, local_rank):
         dist.all_gather(gathered, mine)       # the only collective: results, once, at the end
 
     # ---- live kernel timing (CUDA events around every launch of the three kernels of interest)
+    os.environ['G6D_BRANCH_STREAMS'] = '0'      # per-kernel timing: one kernel at a time, no co-scheduling
     device_step(eager=True)
     torch.cuda.synchronize()
     prof = ops.enable_profiling()
@@ -261,6 +262,7 @@ def run_ours(args, rank, world, local_rank):
     torch.cuda.synchronize()
     eager_ms = pe0.elapsed_time(pe1)
     stats = ops.collect_profile(prof)
+    os.environ.pop('G6D_BRANCH_STREAMS', None)
     peaks = read_peaks()
     conv = stats.get('g6d_conv_tc', {'ms': 0, 'work': 0, 'n': 1})
     ffma = stats.get('g6d_conv', {'ms': 0, 'work': 0, 'n': 0})

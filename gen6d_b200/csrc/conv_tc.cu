@@ -729,6 +729,18 @@ conv_tcflat_kernel(const ConvFlatP p, const __grid_constant__ CUtensorMap map_hi
     }
 }
 
+// G6D_CONV_FLAT: 0 = never use the A-reuse kernel, 1 = FLAT mode only (default), 2 = FLAT and ROW.
+// Measured on B200 (tools/conv_breakdown.py): the 3xTF32 MMAs are shared-memory-bandwidth bound
+// (every MMA re-reads 4 KB of A and N*32 B of B; at N = 128 that alone is 128 B/clk/SM), so the
+// 3x-reuse ROW mode does not pay for its junk columns, while FLAT (9x reuse, and the prologue
+// applied once per element instead of once per tap) gains 26 % on the selector's first tower conv.
+static int flat_level() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("G6D_CONV_FLAT"); v = (e && e[0] >= '0' && e[0] <= '2') ? e[0] - '0' : 1; }
+    return v;
+}
+static bool flat_disabled() { return flat_level() == 0; }
+
 static int fill_flat_params(const g6d_conv_desc* d, ConvFlatP& p, int* smem_bytes) {
     if (!d || d->stride != 1 || (d->Cin % TC_BK) != 0 || d->Cout < 16 || (d->in_cstride & 3) || (d->in_coff & 3)) return -1;
     const int Do = d->D + 2 * d->pd - d->kd + 1, Ho = d->H + 2 * d->ph - d->kh + 1, Wo = d->W + 2 * d->pw - d->kw + 1;
@@ -750,7 +762,7 @@ static int fill_flat_params(const g6d_conv_desc* d, ConvFlatP& p, int* smem_byte
     int mode, rows, ntab;
     // FLAT when two A stages of the full halo + >= 3 B stages fit
     if (2 * a_stage(flat_rows) + 3 * b_stage + 4 * flat_rows + 2048 <= budget) { mode = 0; rows = flat_rows; ntab = 1; }
-    else if (d->kw > 1) { mode = 1; rows = row_rows; ntab = d->kh; }
+    else if (d->kw > 1 && flat_level() >= 2) { mode = 1; rows = row_rows; ntab = d->kh; }
     else return -1;
     p.B = d->B; p.D = d->D; p.H = d->H; p.W = d->W; p.Cin = d->Cin; p.ics = d->in_cstride; p.ico = d->in_coff;
     p.Cout = d->Cout; p.kd = d->kd; p.kh = d->kh; p.kw = d->kw; p.pd = d->pd; p.ph = d->ph; p.pw = d->pw;
@@ -820,11 +832,7 @@ extern "C" int g6d_conv_tc_supported(const g6d_conv_desc* d) {
     return (d->Cin % TC_BK) == 0 && d->Cout >= 16 && (d->in_cstride & 3) == 0 && (d->in_coff & 3) == 0 ? 1 : 0;
 }
 
-static bool flat_disabled() {
-    static int v = -1;
-    if (v < 0) { const char* e = getenv("G6D_CONV_FLAT"); v = (e && e[0] == '0') ? 1 : 0; }
-    return v == 1;
-}
+
 
 extern "C" long long g6d_conv_tc_workspace_bytes(const g6d_conv_desc* desc) {
     {

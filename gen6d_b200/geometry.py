@@ -182,11 +182,14 @@ def select_views_fps(database, ids, count):
 def select_views_near_pose(database, center, ids, pose, count=6, even=False, even_count=128):
     """database_utils.py:125-139: optionally re-spread with FPS, then the `count` views whose
     viewing direction is closest (largest cosine) to that of `pose`."""
-    ids = np.asarray(ids)
-    poses = np.asarray([database.get_pose(i) for i in ids])
-    if even:
-        keep = farthest_point_indices(np.asarray([camera_center(p) for p in poses]), even_count + 1)
-        ids, poses = ids[keep], poses[keep]
+    if even and hasattr(database, 'even_subset'):
+        ids, poses = database.even_subset(ids, even_count)
+    else:
+        ids = np.asarray(ids)
+        poses = np.asarray([database.get_pose(i) for i in ids])
+        if even:
+            keep = farthest_point_indices(np.asarray([camera_center(p) for p in poses]), even_count + 1)
+            ids, poses = ids[keep], poses[keep]
     unit = lambda v: v / np.linalg.norm(v, 2, -1, keepdims=True)
     dirs = unit(np.asarray([camera_center(p) for p in poses]) - center[None])
     q = unit(camera_center(pose) - center)
@@ -256,6 +259,8 @@ class NormalizedView:
         self.db = database
         self.scale = 2.0 / database.object_diameter()
         self.offset = -self.scale * database.object_center()
+        self._poses = {}        # normalised poses, cached (pose-independent of the query)
+        self._even = {}         # FPS-resampled reference subsets per (ids, count)
 
     def normalize_pose(self, pose):
         R, t = pose[:3, :3], pose[:3, 3]
@@ -266,7 +271,20 @@ class NormalizedView:
         return np.concatenate([R, (R @ self.offset / self.scale + t / self.scale)[:, None]], -1).astype(np.float32)
 
     def get_pose(self, i):
-        return self.normalize_pose(self.db.get_pose(i))
+        if i not in self._poses:
+            self._poses[i] = self.normalize_pose(self.db.get_pose(i))
+        return self._poses[i]
+
+    def even_subset(self, ids, count):
+        """The FPS re-spread of database_utils.py:129-134 depends only on the reference set, not on
+        the query pose: computed once per (ids, count) instead of once per refinement iteration."""
+        key = (tuple(ids), count)
+        if key not in self._even:
+            ids_a = np.asarray(ids)
+            poses = np.asarray([self.get_pose(i) for i in ids_a])
+            keep = farthest_point_indices(np.asarray([camera_center(p) for p in poses]), count + 1)
+            self._even[key] = (ids_a[keep], poses[keep])
+        return self._even[key]
 
     def get_K(self, i):
         return self.db.get_K(i)
@@ -284,11 +302,21 @@ class NormalizedView:
         return self.db.object_vert()
 
 
+_VIEW_CACHE = {}
+
+
+def _normalized_view(database):
+    key = id(database)
+    if key not in _VIEW_CACHE or _VIEW_CACHE[key].db is not database:
+        _VIEW_CACHE[key] = NormalizedView(database)
+    return _VIEW_CACHE[key]
+
+
 def refine_problem(database, ref_ids, que_img, que_K, in_pose, size=128, ref_num=6, ref_even=False, margin=0.05):
     """Everything refiner.py:285-325 prepares on the host for one refinement step: the query
     look-at crop at the input pose and the `ref_num` nearest reference views re-rendered with
     their in-plane orientation aligned to it."""
-    view = NormalizedView(database)
+    view = _normalized_view(database)
     pose_n = view.normalize_pose(in_pose)
     center = view.object_center()
     f_look = look_at_point(pose_n, que_K, center)[1]

@@ -69,6 +69,41 @@ class PackedModule(nn.Module):
         return t.cpu().numpy()
 
 
+class Branches:
+    """Fork/join of independent sub-graphs onto side streams (the four detector scales, the three
+    selector towers, the refiner's feature branches).  At batch 1 most of their kernels launch far
+    fewer CTAs than the 148 SMs, so running the branches concurrently is what fills the machine.
+    Works eagerly and under CUDA-graph capture (the side streams fork from and join back into the
+    capturing stream, so the captured graph gets parallel branches).  Branch results must be kept
+    alive by the caller until they have been consumed on the main stream.  G6D_BRANCH_STREAMS=0
+    serialises everything on the current stream."""
+    _pool = {}
+
+    def __init__(self, n):
+        import os
+        self.enabled = os.environ.get('G6D_BRANCH_STREAMS', '1') != '0' and n > 1
+        self.main = torch.cuda.current_stream()
+        if self.enabled:
+            dev = torch.cuda.current_device()
+            pool = Branches._pool.setdefault(dev, [])
+            while len(pool) < n:
+                pool.append(torch.cuda.Stream())
+            self.streams = pool[:n]
+            for st in self.streams:
+                st.wait_stream(self.main)
+
+    def run(self, i, fn):
+        if not self.enabled:
+            return fn()
+        with torch.cuda.stream(self.streams[i]):
+            return fn()
+
+    def join(self):
+        if self.enabled:
+            for st in self.streams:
+                self.main.wait_stream(st)
+
+
 def linear_as_conv(weight, bias, cin_pad=None):
     """nn.Linear / Conv1d(k=1) / Conv2d(k=1) weight -> PackedConv of a 1x1 convolution."""
     w = weight.reshape(weight.shape[0], weight.shape[1], 1)

@@ -6,7 +6,7 @@ import torch
 
 from .. import ops
 from .backbone import pack_vgg, vgg_v1
-from .base import PackedModule
+from .base import Branches, PackedModule
 from .params import VGG11BNParams, detector_heads
 
 
@@ -88,21 +88,32 @@ class Detector(PackedModule):
         p = self.packed()
         qn, hq, wq, _ = que01.shape
         hs, ws = hq // 8, wq // 8
-        maps, sizes = [], []
-        for ht, wt in self.scale_sizes(hq, wq):
+        scales = self.scale_sizes(hq, wq)
+        br = Branches(len(scales))          # the scales are independent until the fused head
+
+        def one_scale(ht, wt):
             cur = que01 if (ht, wt) == (hq, wq) else ops.resize_bilinear(que01, ht, wt)
-            raw = self._raw_correlation(cur)
-            maps.append(raw)
-            sizes.append([(r.shape[1], r.shape[2]) for r in raw])
+            return self._raw_correlation(cur)
+
+        maps = [br.run(i, lambda ht=ht, wt=wt: one_scale(ht, wt)) for i, (ht, wt) in enumerate(scales)]
+        br.join()
+        sizes = [[(r.shape[1], r.shape[2]) for r in raw] for raw in maps]
         rfn = self.ref_kernels[0].cout
         feats = ops.det_score_fuse(maps, sizes, rfn, hs, ws, self.cfg['vgg_score_stats'], self.cfg['vgg_score_max'],
                                    p['w1'], p['b1'], p['w2'], p['b2'], qn)
         outs = {}
-        for head in ('score_predict', 'scale_predict', 'offset_predict'):
+        heads = ('score_predict', 'scale_predict', 'offset_predict')
+        hb = Branches(len(heads))
+
+        def one_head(head):
             x = feats
             for i, pc in enumerate(p[head]):
                 x = ops.conv(x, pc, act=ops.ACT_RELU if i < 2 else ops.ACT_NONE)
-            outs[head] = x
+            return x
+
+        for i, head in enumerate(heads):
+            outs[head] = hb.run(i, lambda head=head: one_head(head))
+        hb.join()
         if return_taps:
             outs['raw'] = maps
             outs['scores_feats'] = feats

@@ -11,7 +11,7 @@ import torch
 
 from .. import ops
 from .backbone import pack_vgg, vgg_v3
-from .base import PackedModule, linear_as_conv
+from .base import Branches, PackedModule, linear_as_conv
 from .params import RefineFeatureParams, RefineRegressorParams, RefineVolumeParams
 
 IN_EPS = 1e-5
@@ -73,13 +73,21 @@ class VolumeRefiner(PackedModule):
         x0, x1, x2 = [ops.l2norm_channels(f) for f in vgg_v3(p['vgg'], imgs_norm4)]
         h, w = x0.shape[1], x0.shape[2]
         cat = torch.empty(n, h, w, 192, device=x0.device, dtype=torch.float32)
-        for bi, (name, x) in enumerate((('conv0', x0), ('conv1', x1), ('conv2', x2))):
+        br, keep = Branches(3), []
+
+        def one_branch(bi, name, x):
             y, ps, pb = self._conv_in_conv(x, p[name], x.shape[1] * x.shape[2])
             if bi == 0:
                 ops.affine_act(y, ps, pb, rows_per_group=h * w, out=cat, out_coff=0)
             else:
                 yn = ops.affine_act(y, ps, pb, rows_per_group=y.shape[1] * y.shape[2])
                 ops.resize_bilinear(yn, h, w, out=cat, out_coff=64 * bi)   # F.interpolate x2 / x4 bilinear
+                keep.append(yn)
+            keep.append((y, ps, pb))
+
+        for bi, (name, x) in enumerate((('conv0', x0), ('conv1', x1), ('conv2', x2))):
+            br.run(bi, lambda bi=bi, name=name, x=x: one_branch(bi, name, x))
+        br.join()
         y, ps, pb = self._conv_in_conv(cat, p['conv_out'], h * w)
         return ops.affine_act(y, ps, pb, rows_per_group=h * w)
 
@@ -88,11 +96,18 @@ class VolumeRefiner(PackedModule):
         p = self.packed()
         qn, sn = mean_in.shape[0], mean_in.shape[1]
         cat = torch.empty(qn, sn, sn, sn, 128, device=mean_in.device, dtype=torch.float32)
-        for bi, (name, x) in enumerate((('mean_embed', mean_in), ('var_embed', stdv))):
+        br, keep = Branches(2), []
+
+        def one_embed(bi, name, x):
             y = ops.conv(x, p[name][0])
             ps, pb = ops.instnorm_stats(y, rows_per_group=sn ** 3, eps=IN_EPS)
             ops.conv(y, p[name][1], prologue=ops.PRO_AFFINE_RELU, pro_scale=ps, pro_shift=pb, group_rows=1,
                      out=cat, out_coff=64 * bi)
+            keep.append((y, ps, pb))
+
+        for bi, (name, x) in enumerate((('mean_embed', mean_in), ('var_embed', stdv))):
+            br.run(bi, lambda bi=bi, name=name, x=x: one_embed(bi, name, x))
+        br.join()
         x, pro, ps, pb = cat, ops.PRO_NONE, None, None
         for pc in p['trunk']:
             y = ops.conv(x, pc, prologue=pro, pro_scale=ps, pro_shift=pb, group_rows=1)

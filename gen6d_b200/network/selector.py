@@ -13,7 +13,7 @@ import torch
 
 from .. import ops
 from .backbone import pack_vgg, vgg_v1
-from .base import PackedModule, linear_as_conv
+from .base import Branches, PackedModule, linear_as_conv
 from .params import SEL_TOWER_POST, SEL_TOWERS, VGG11BNParams, selector_modules
 
 IN_EPS = 1e-5
@@ -171,11 +171,18 @@ class ViewpointSelector(PackedModule):
         feats = torch.zeros(S, FEAT_PAD, device=dev, dtype=torch.float32)
         scores = ops.sel_corr_score3([r.reshape(S, -1, r.shape[-1]) for r in self.ref_feats_cache],
                                      [q.reshape(-1, q.shape[-1]) for q in q_feats])
-        for l, (q, ref, (s1, s2)) in enumerate(zip(q_feats, self.ref_feats_cache, self.ref_sums)):
+        br = Branches(3 if self.comm.world == 1 else 1)     # the three towers only meet in cat_buf
+        keep = []
+
+        def one_level(l, q, ref, s1, s2):
             h, w, c = q.shape
-            q2 = q.reshape(h * w, c)
-            scale, shift = ops.sel_corr_prologue(q2, s1, s2, S_total, IN_EPS)
+            scale, shift = ops.sel_corr_prologue(q.reshape(h * w, c), s1, s2, S_total, IN_EPS)
+            keep.append((scale, shift))
             self._tower(l, ref, scale, shift, cat_buf, S)
+
+        for l, (q, ref, (s1, s2)) in enumerate(zip(q_feats, self.ref_feats_cache, self.ref_sums)):
+            br.run(l, lambda l=l, q=q, ref=ref, s1=s1, s2=s2: one_level(l, q, ref, s1, s2))
+        br.join()
         # corr_feats_conv (selector.py:71-77): 1x1 768->512, IN, ReLU, 1x1 512->512, AvgPool(4,4).
         # The second 1x1 conv is linear, so the 4x4 average is taken first (16x less work).
         y = ops.conv(cat_buf, p['cf0'])
