@@ -26,6 +26,7 @@ struct VolParams {
 // 128 B/clk L1 -> ~13 us per pose on 148 SMs, above the 8.2 us pure-HBM time.
 constexpr int kViewsMax = kMaxRefViews;   // views = R references + the query (view index R) <= 8
 
+template <int RT>   // RT > 0: number of reference views known at compile time (6 on the estimator path); 0: runtime
 __global__ void __launch_bounds__(256, 3) ref_volume_fill_kernel(const VolParams p) {
     __shared__ float sP[kViewsMax][12];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -37,13 +38,14 @@ __global__ void __launch_bounds__(256, 3) ref_volume_fill_kernel(const VolParams
     const int bk = b % nbk; b /= nbk;
     const int bj = b % nbj;
     const int bi = b / nbj;
-    const int nviews = p.R + 1;
+    const int R = RT > 0 ? RT : p.R;
+    const int nviews = R + 1;
 
     // P_v = K_v @ [R|t]_v for the R references and the query of this pose (refiner.py:227,243)
     if (threadIdx.x < nviews * 12) {
         const int v = threadIdx.x / 12, e = threadIdx.x % 12, r = e / 4, c = e % 4;
-        const float* K = v < p.R ? p.ref_Ks + ((long long)qi * p.R + v) * 9 : p.que_Ks + (long long)qi * 9;
-        const float* T = v < p.R ? p.ref_poses + ((long long)qi * p.R + v) * 12 : p.que_poses + (long long)qi * 12;
+        const float* K = v < R ? p.ref_Ks + ((long long)qi * R + v) * 9 : p.que_Ks + (long long)qi * 9;
+        const float* T = v < R ? p.ref_poses + ((long long)qi * R + v) * 12 : p.que_poses + (long long)qi * 12;
         sP[v][e] = fmaf(K[r * 3 + 0], T[c], fmaf(K[r * 3 + 1], T[4 + c], K[r * 3 + 2] * T[8 + c]));
     }
     __syncthreads();
@@ -57,7 +59,7 @@ __global__ void __launch_bounds__(256, 3) ref_volume_fill_kernel(const VolParams
     const float step = 2.f / (float)(sn - 1);
     auto lin = [&](int a) { return a < sn / 2 ? -1.f + step * (float)a : 1.f - step * (float)(sn - 1 - a); };
     const long long fsz = (long long)p.fh * p.fw * p.C;
-    const float* ref_base = p.ref_feats + (long long)qi * p.R * fsz;
+    const float* ref_base = p.ref_feats + (long long)qi * R * fsz;
     const float* que_base = p.que_feats + (long long)qi * fsz;
     const long long nvox = (long long)sn * sn * sn;
 
@@ -107,21 +109,23 @@ __global__ void __launch_bounds__(256, 3) ref_volume_fill_kernel(const VolParams
 #pragma unroll
                 for (int v = 0; v < kViewsMax; ++v) {
                     if (v < nviews) {
-                        const float* fmap = v < p.R ? ref_base + (long long)v * fsz : que_base;
-                        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+                        // 32-bit element offsets from one base per tensor; the tap offset arrives by shuffle
+                        const float* fmap = v < R ? ref_base + v * (int)fsz + c : que_base + c;
                         float4 f[4]; float w[4];
 #pragma unroll
                         for (int t = 0; t < 4; ++t) {
                             const int idx = __shfl_sync(0xffffffffu, tidx[t], v * 4 + vq);
                             w[t] = __shfl_sync(0xffffffffu, tw[t], v * 4 + vq);
-                            f[t] = __ldg(reinterpret_cast<const float4*>(fmap + idx + c));
+                            f[t] = __ldg(reinterpret_cast<const float4*>(fmap + idx));
                         }
+                        float4 acc;
+                        acc.x = f[0].x * w[0]; acc.y = f[0].y * w[0]; acc.z = f[0].z * w[0]; acc.w = f[0].w * w[0];
 #pragma unroll
-                        for (int t = 0; t < 4; ++t) {
+                        for (int t = 1; t < 4; ++t) {
                             acc.x = fmaf(f[t].x, w[t], acc.x); acc.y = fmaf(f[t].y, w[t], acc.y);
                             acc.z = fmaf(f[t].z, w[t], acc.z); acc.w = fmaf(f[t].w, w[t], acc.w);
                         }
-                        if (v < p.R) {
+                        if (v < R) {
                             s[v] = acc;
                             mean.x += acc.x; mean.y += acc.y; mean.z += acc.z; mean.w += acc.w;
                         } else {
@@ -129,12 +133,12 @@ __global__ void __launch_bounds__(256, 3) ref_volume_fill_kernel(const VolParams
                         }
                     }
                 }
-                const float fr = (float)p.R;
-                mean.x /= fr; mean.y /= fr; mean.z /= fr; mean.w /= fr;
+                const float inv_r = 1.f / (float)R;            // mean = sum * (1/R): within 1 ulp of sum / R
+                mean.x *= inv_r; mean.y *= inv_r; mean.z *= inv_r; mean.w *= inv_r;
                 float4 var = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
                 for (int v = 0; v < kViewsMax; ++v) {
-                    if (v < p.R) {
+                    if (v < R) {
                         float d;
                         d = s[v].x - mean.x; var.x = fmaf(d, d, var.x);
                         d = s[v].y - mean.y; var.y = fmaf(d, d, var.y);
@@ -142,9 +146,9 @@ __global__ void __launch_bounds__(256, 3) ref_volume_fill_kernel(const VolParams
                         d = s[v].w - mean.w; var.w = fmaf(d, d, var.w);
                     }
                 }
-                const float fu = (float)(p.R - 1);  // unbiased (torch.std default, refiner.py:237)
+                const float inv_u = 1.f / (float)(R - 1);      // unbiased (torch.std default, refiner.py:237)
                 float4 sd;
-                sd.x = sqrtf(var.x / fu); sd.y = sqrtf(var.y / fu); sd.z = sqrtf(var.z / fu); sd.w = sqrtf(var.w / fu);
+                sd.x = sqrtf(var.x * inv_u); sd.y = sqrtf(var.y * inv_u); sd.z = sqrtf(var.z * inv_u); sd.w = sqrtf(var.w * inv_u);
                 float* mrow = p.mean_in + orow * (2 * p.C);
                 __stcs(reinterpret_cast<float4*>(mrow + c), mean);
                 __stcs(reinterpret_cast<float4*>(mrow + p.C + c), qs);
@@ -191,7 +195,8 @@ extern "C" int g6d_ref_volume_fill(const float* ref_feats, const float* que_feat
                 Q, R, fh, fw, C, sn, img_h, img_w};
     G6D_REQUIRE(R <= 7, "g6d_ref_volume_fill: at most 7 reference views (7 + query fill the 8 projection lanes x 4 voxels)");
     const long long bricks = (long long)((sn + 1) / 2) * ((sn + 3) / 4) * ((sn + 7) / 8);
-    ref_volume_fill_kernel<<<(unsigned)(Q * bricks), 256, 0, as_stream(stream)>>>(p);
+    if (R == 6) ref_volume_fill_kernel<6><<<(unsigned)(Q * bricks), 256, 0, as_stream(stream)>>>(p);
+    else ref_volume_fill_kernel<0><<<(unsigned)(Q * bricks), 256, 0, as_stream(stream)>>>(p);
     G6D_CHECK_LAUNCH("g6d_ref_volume_fill");
     return G6D_OK;
 }
