@@ -52,8 +52,8 @@ template <int BN> struct TcCfg {
     // Each tensor-core accumulate truncates to fp32; spreading the K-blocks over several shorter,
     // smaller-magnitude chains (summed in fp32 round-to-nearest by the epilogue) divides the
     // resulting bias on same-sign data by ~NMAIN at no cost.
-    static constexpr int NMAIN = BN == 32 ? 7 : 3;
-    static constexpr int TMEM_COLS = (NMAIN + 1) * BN;             // 256 / 256 / 512 columns
+    static constexpr int NMAIN = BN == 32 ? 7 : (BN == 256 ? 1 : 3);
+    static constexpr int TMEM_COLS = (NMAIN + 1) * BN;             // 256 / 256 / 512 / 512 columns
 };
 
 // ------------------------------------------------------------------------------------------ kernel
@@ -381,7 +381,16 @@ static int make_weight_map(CUtensorMap* map, const float* w, int rows, int K, in
     return G6D_OK;
 }
 
-static int tc_block_n(int Cout) { return Cout > 64 ? 128 : (Cout > 32 ? 64 : 32); }
+// N = 256 tiles (instantiated, selectable with G6D_CONV_N256=1) halve the A re-reads per flop but leave
+// room for only 2 pipeline stages and halve the CTA count: measured 18.4 vs 13.2 ms of convolution
+// time per step on B200, so N <= 128 stays the default.
+static int tc_block_n(int Cout) {
+    static int n256 = -1;
+    if (n256 < 0) { const char* e = getenv("G6D_CONV_N256"); n256 = (e && e[0] == '1') ? 1 : 0; }
+    if (n256 && Cout > 128) return 256;
+    return Cout > 64 ? 128 : (Cout > 32 ? 64 : 32);
+}
+static int flat_block_n(int Cout) { return Cout > 64 ? 128 : (Cout > 32 ? 64 : 32); }   // A-reuse kernel: smem goes to the halo
 
 static int fill_tc_params(const g6d_conv_desc* d, ConvTcP& p) {
     G6D_REQUIRE(d != nullptr, "g6d_conv_tc: null desc");
@@ -746,7 +755,7 @@ static int fill_flat_params(const g6d_conv_desc* d, ConvFlatP& p, int* smem_byte
     const int Do = d->D + 2 * d->pd - d->kd + 1, Ho = d->H + 2 * d->ph - d->kh + 1, Wo = d->W + 2 * d->pw - d->kw + 1;
     if (Do != d->Do || Ho != d->Ho || Wo != d->Wo || Do < 1 || Ho < 1 || Wo < 1) return -1;
     if (d->kd * d->kh * d->kw == 1) return -1;                        // 1x1: nothing to reuse, old kernel
-    const int bn = d->Cout > 64 ? 128 : (d->Cout > 32 ? 64 : 32);
+    const int bn = flat_block_n(d->Cout);
     const int Wp = d->W + 2 * d->pw;
     const int flat_rows = TC_BM + (d->kh - 1) * Wp + d->kw - 1;
     const int row_rows = TC_BM + d->kw - 1;
@@ -856,7 +865,7 @@ extern "C" int g6d_conv_tc(const g6d_conv_desc* desc, const float* x, const floa
             if (fp.pro != G6D_PRO_NONE) G6D_REQUIRE(pro_scale && pro_shift, "g6d_conv_tc: prologue operands missing");
             if (fp.splits > 1) G6D_REQUIRE(ws != nullptr, "g6d_conv_tc: split workspace required (%d splits)", fp.splits);
             fp.x = x; fp.bias = bias; fp.ps = pro_scale; fp.pb = pro_shift; fp.y = y; fp.ws = (float*)ws;
-            const int bn = tc_block_n(fp.Cout);
+            const int bn = flat_block_n(fp.Cout);
             const int K = fp.kd * fp.kh * fp.kw * fp.Cin;
             CUtensorMap mh, ml;
             int rc2;
@@ -888,7 +897,8 @@ extern "C" int g6d_conv_tc(const g6d_conv_desc* desc, const float* x, const floa
     if ((rc = make_weight_map(&mh, w_hi, w_rows, p.K, bn)) != G6D_OK) return rc;
     if ((rc = make_weight_map(&ml, w_lo, w_rows, p.K, bn)) != G6D_OK) return rc;
     cudaStream_t st = as_stream(stream);
-    if (bn == 128) rc = launch_tc<128>(p, mh, ml, st);
+    if (bn == 256) rc = launch_tc<256>(p, mh, ml, st);
+    else if (bn == 128) rc = launch_tc<128>(p, mh, ml, st);
     else if (bn == 64) rc = launch_tc<64>(p, mh, ml, st);
     else rc = launch_tc<32>(p, mh, ml, st);
     if (rc != G6D_OK) return rc;

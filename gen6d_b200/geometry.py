@@ -196,33 +196,69 @@ def select_views_near_pose(database, center, ids, pose, count=6, even=False, eve
     return ids[np.argsort(-(dirs @ q))[:count]]
 
 
+def _look_at_batch(cen_px, Ks):
+    """Vectorised look_at_pixel: cen_px [n,2], Ks [n,3,3] -> (R [n,3,3], f [n])."""
+    f = (Ks[:, 0, 0] + Ks[:, 1, 1]) / 2
+    c = cen_px - Ks[:, :2, 2]
+    xy = c / f[:, None]
+    a, b = -np.arctan2(xy[:, 0], 1.0), np.arctan2(xy[:, 1], 1.0)
+    ca, sa, cb, sb = np.cos(a), np.sin(a), np.cos(b), np.sin(b)
+    z, o = np.zeros_like(a), np.ones_like(a)
+    ry = np.stack([np.stack([ca, z, sa], -1), np.stack([z, o, z], -1), np.stack([-sa, z, ca], -1)], 1)
+    rx = np.stack([np.stack([o, z, z], -1), np.stack([z, cb, -sb], -1), np.stack([z, sb, cb], -1)], 1)
+    return rx @ ry, np.sqrt(np.sum(c * c, 1) + f * f)
+
+
+def _project_center_batch(center, poses, Ks):
+    p = (poses[:, :, :3] @ center + poses[:, :, 3])[:, None, :] @ np.transpose(Ks, (0, 2, 1))
+    p = p[:, 0]
+    d = p[:, 2].copy()
+    tiny = (np.abs(d) < 1e-4) & (np.abs(d) > 0)
+    d[tiny] = 1e-4
+    return p[:, :2] / d[:, None]
+
+
 def normalize_reference_views(database, ids, size, margin, align_pose=None, align_K=None):
     """database_utils.py:54-110 (rectify_rot=True, no extra rotations): every reference view is
     re-rendered as a look-at crop of the object at a common apparent size, with the in-plane
     orientation either 'object-up' (build time) or aligned to a given pose (refinement).
-    Returns imgs [n,size,size,3] u8, Ks, poses, Hs (masks are not used on the inference path)."""
+    Returns imgs [n,size,size,3] u8, Ks, poses, Hs (masks are not used on the inference path).
+    The camera algebra is batched over the views (float64); only the warps loop."""
     center = database.object_center().astype(np.float64)
     diameter = database.object_diameter()
-    imgs, Ks, poses, Hs = [], [], [], []
-    for i in ids:
-        pose, K = database.get_pose(i), database.get_K(i)
-        cen_px = project(center[None], pose, K)[0][0]
-        dist = np.linalg.norm(camera_center(pose) - center)
-        f_look = look_at_point(pose, K, center)[1]
-        scale = size * (1 - margin) / diameter * dist / f_look
-        if align_pose is not None:
-            angle = inplane_angle_between(pose, K, align_pose, align_K, center)
-        else:
-            v = (pose[:, :3] @ database.object_vert())[:2].astype(np.float64)
-            if np.linalg.norm(v) < 1e-5:
-                v = v + 1e-5 * np.sign(v)
-            angle = -np.arctan2(v[1], v[0]) - np.pi / 2
-        img, K_new, pose_new, _, H = look_at_crop(database.get_image(i), K, pose, cen_px, angle, scale, size, size)
-        imgs.append(img)
-        Ks.append(K_new)
-        poses.append(pose_new)
-        Hs.append(H)
-    return np.stack(imgs, 0), np.stack(Ks, 0), np.stack(poses, 0), np.stack(Hs, 0)
+    poses = np.stack([database.get_pose(i) for i in ids], 0).astype(np.float64)
+    Ks = np.stack([database.get_K(i) for i in ids], 0).astype(np.float64)
+    n = len(ids)
+    cen_px = _project_center_batch(center, poses, Ks)
+    cams = -np.einsum('nji,nj->ni', poses[:, :, :3], poses[:, :, 3])
+    dist = np.linalg.norm(cams - center[None], axis=1)
+    R_look, f_look = _look_at_batch(cen_px, Ks)
+    scale = size * (1 - margin) / diameter * dist / f_look
+    if align_pose is not None:
+        ap, aK = align_pose.astype(np.float64), align_K.astype(np.float64)
+        Rq = look_at_point(ap, aK, center)[0] @ ap[:, :3]
+        rel = Rq[None] @ np.transpose(R_look @ poses[:, :, :3], (0, 2, 1))
+        # R = Rx(c) Ry(b) Rz(a)  =>  first row = [cos b cos a, -cos b sin a, sin b]
+        angle = np.arctan2(-rel[:, 0, 1], rel[:, 0, 0])
+    else:
+        v = (poses[:, :, :3] @ database.object_vert().astype(np.float64))[:, :2]
+        small = np.linalg.norm(v, axis=1) < 1e-5
+        v[small] += 1e-5 * np.sign(v[small])
+        angle = -np.arctan2(v[:, 1], v[:, 0]) - np.pi / 2
+    ca, sa = np.cos(angle), np.sin(angle)
+    z, o = np.zeros(n), np.ones(n)
+    Rz = np.stack([np.stack([ca, -sa, z], -1), np.stack([sa, ca, z], -1), np.stack([z, z, o], -1)], 1).astype(np.float32)
+    R = Rz @ R_look                                            # reference builds R_z in float32
+    f = f_look * scale
+    K_new = np.zeros((n, 3, 3), np.float32)
+    K_new[:, 0, 0] = K_new[:, 1, 1] = f
+    K_new[:, 0, 2], K_new[:, 1, 2], K_new[:, 2, 2] = size / 2, size / 2, 1
+    Hs = K_new @ R @ np.linalg.inv(Ks)
+    rect = R.astype(np.float32)
+    poses_new = np.concatenate([rect @ poses[:, :, :3], rect @ poses[:, :, 3:]], 2)
+    imgs = np.stack([cv2.warpPerspective(database.get_image(i), Hs[k], (size, size), flags=cv2.INTER_LINEAR)
+                     for k, i in enumerate(ids)], 0)
+    return imgs, K_new, poses_new, Hs
 
 
 # ------------------------------------------------------------------------------------------ pose from detection + selection
