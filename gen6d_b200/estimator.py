@@ -99,4 +99,38 @@ class Gen6DEstimator:
         return pose, inter
 
 
+    # ------------------------------------------------------------------ throughput API
+    def worker_clone(self):
+        import copy
+        other = copy.copy(self)
+        other.detector, other.selector = self.detector.worker_clone(), self.selector.worker_clone()
+        other.refiner = self.refiner.worker_clone() if self.refiner is not None else None
+        return other
+
+    def predict_many(self, que_imgs, que_Ks, workers=2):
+        """Poses for independent frames, `workers` frames in flight: each worker thread owns a clone
+        of the networks (shared weights / reference features, private CUDA graphs) and a CUDA
+        stream, so one frame's host geometry (OpenCV warps, view selection) overlaps another frame's
+        kernels.  Same per-frame computation and results as predict(); returns [(pose, inter)]."""
+        from concurrent.futures import ThreadPoolExecutor
+        if not hasattr(self, '_workers') or len(self._workers) != workers:
+            self._workers = [(self.worker_clone(), torch.cuda.Stream()) for _ in range(workers)]
+            self._pool = ThreadPoolExecutor(workers)
+            for est, stream in self._workers:        # capture every worker's stage graphs one at a time
+                with torch.cuda.stream(stream):
+                    est.predict(que_imgs[0], que_Ks[0])
+                    stream.synchronize()
+        results = [None] * len(que_imgs)
+
+        def run(w):
+            est, stream = self._workers[w]
+            with torch.cuda.stream(stream):
+                for i in range(w, len(que_imgs), workers):
+                    results[i] = est.predict(que_imgs[i], que_Ks[i])
+                stream.synchronize()
+
+        list(self._pool.map(run, range(workers)))
+        return results
+
+
 name2estimator = {'gen6d': Gen6DEstimator}

@@ -34,7 +34,8 @@ class CapturedStage:
         torch.cuda.synchronize()
         self.graph = torch.cuda.CUDAGraph()
         before = _lib.launch_count()
-        with torch.cuda.graph(self.graph), torch.no_grad():
+        # thread_local: other host threads (predict_many workers) may keep issuing CUDA calls meanwhile
+        with torch.cuda.graph(self.graph, capture_error_mode='thread_local'), torch.no_grad():
             self.static_out = fn(*self.static_in)
         self.kernels = _lib.launch_count() - before     # kernel nodes captured (our C-ABI launches)
 

@@ -8,7 +8,6 @@ from ..graphs import StageCache
 
 
 IO_BYTES = {'h2d': 0, 'd2h': 0}   # bytes moved through the numpy-facing API (bench.py reads this)
-_PINNED, _PINNED_NEXT = {}, {}
 
 
 class PackedModule(nn.Module):
@@ -19,6 +18,7 @@ class PackedModule(nn.Module):
         super().__init__()
         self._packed = None
         self.stages = StageCache()      # CUDA graphs of the fixed-shape numpy-API stages
+        self._pinned, self._pinned_next = {}, {}
         self.register_load_state_dict_post_hook(lambda module, keys: module.invalidate_packed())
 
     def invalidate_packed(self):
@@ -47,17 +47,28 @@ class PackedModule(nn.Module):
     def _pack(self):
         raise NotImplementedError
 
+    def worker_clone(self):
+        """A second handle on the same network for another host thread / CUDA stream: parameters,
+        packed weights and cached reference features are shared (read-only on the device); the
+        CUDA-graph stages (static buffers) and pinned staging buffers are private."""
+        import copy
+        self.packed()
+        other = copy.copy(self)
+        other.stages = StageCache()
+        other._pinned, other._pinned_next = {}, {}
+        return other
+
     def _to_dev(self, array, dtype=None):
         """numpy -> device through a cached pinned staging buffer (async H2D on the current stream)."""
         t = torch.from_numpy(np.ascontiguousarray(array))
         if dtype is not None:
             t = t.to(dtype)
         key = (tuple(t.shape), t.dtype)
-        ring = _PINNED.setdefault(key, [])
+        ring = self._pinned.setdefault(key, [])
         if len(ring) < 4:
             ring.append(torch.empty(t.shape, dtype=t.dtype).pin_memory())
-        slot = ring[_PINNED_NEXT.get(key, 0) % len(ring)]
-        _PINNED_NEXT[key] = _PINNED_NEXT.get(key, 0) + 1
+        slot = ring[self._pinned_next.get(key, 0) % len(ring)]
+        self._pinned_next[key] = self._pinned_next.get(key, 0) + 1
         slot.copy_(t)
         IO_BYTES['h2d'] += t.numel() * t.element_size()
         return slot.to(self.device, non_blocking=True)

@@ -57,3 +57,14 @@ def test_tracking_refinement_matches_reference(est):
     print('per-iteration max |dR|', err_r, 'relative |dt|', err_t)
     np.testing.assert_allclose(got[:, :, :3], want[:, :, :3], atol=1e-2)
     assert (err_t < 1e-2).all()
+
+
+def test_predict_many_equals_predict(est):
+    """The pipelined throughput API returns exactly what per-frame predict() returns."""
+    e, db = est
+    ids = db.get_img_ids()[:4]
+    imgs, Ks = [db.get_image(i) for i in ids], [db.get_K(i) for i in ids]
+    seq = [e.predict(im, K)[0] for im, K in zip(imgs, Ks)]
+    par = e.predict_many(imgs, Ks, workers=2)
+    for a, (b, _) in zip(seq, par):
+        np.testing.assert_allclose(a, b, atol=1e-5)
