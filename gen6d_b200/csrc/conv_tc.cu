@@ -335,6 +335,321 @@ conv_tc_kernel(const ConvTcP p, const __grid_constant__ CUtensorMap map_hi, cons
     }
 }
 
+// ==========================================================================================
+// conv_tc2_kernel: persistent version of conv_tc_kernel.
+//   * one CTA per SM loops over (M tile, N tile, K split) work items, so there is no wave tail and
+//     the per-CTA set-up (TMEM allocation, barrier init, descriptor prefetch) is paid once;
+//   * two TMEM accumulator buffers: the MMA warp starts the next tile while four dedicated
+//     epilogue warps drain the previous one (tmem_full / tmem_empty barriers);
+//   * the eight producer warps keep a two-deep register prefetch (loads of K-blocks it+1, it+2 in
+//     flight while K-block it is transformed and stored);
+//   * the smem ring never drains between tiles (one global K-block counter).
+// Warps: 0-7 A producers, 8 B producer (TMA), 9 MMA issuer + TMEM owner, 10-13 epilogue.
+constexpr int TC2_THREADS = 14 * 32;
+
+template <int BN> struct Tc2Cfg {
+    static constexpr int A_BYTES = TC_BM * 128;
+    static constexpr int B_BYTES = BN * 128;
+    static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
+    static constexpr int STAGES = (208 * 1024) / STAGE_BYTES > 6 ? 6 : (208 * 1024) / STAGE_BYTES;
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256;
+    static constexpr int NMAIN = BN == 32 ? 7 : (BN == 64 ? 3 : 1);      // per accumulator buffer
+    static constexpr int BUF_COLS = (NMAIN + 1) * BN;                     // 256
+    static constexpr int TMEM_COLS = 2 * BUF_COLS;                        // 512: two buffers
+};
+
+struct Tc2Work { int m_tiles, n_tiles, total; };
+
+template <int BN>
+__global__ void __launch_bounds__(TC2_THREADS, 1)
+conv_tc2_kernel(const ConvTcP p, const Tc2Work wk, const __grid_constant__ CUtensorMap map_hi,
+                const __grid_constant__ CUtensorMap map_lo) {
+    using Cfg = Tc2Cfg<BN>;
+    constexpr int STAGES = Cfg::STAGES;
+    constexpr int NMAIN = Cfg::NMAIN;
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t* base_ptr = smem_raw + (base - smem_u32(smem_raw));
+    const uint32_t bar_base = base + STAGES * Cfg::STAGE_BYTES;
+    auto a_hi = [&](int s) { return base + s * Cfg::STAGE_BYTES; };
+    auto a_lo = [&](int s) { return base + s * Cfg::STAGE_BYTES + Cfg::A_BYTES; };
+    auto b_hi = [&](int s) { return base + s * Cfg::STAGE_BYTES + 2 * Cfg::A_BYTES; };
+    auto b_lo = [&](int s) { return base + s * Cfg::STAGE_BYTES + 2 * Cfg::A_BYTES + Cfg::B_BYTES; };
+    auto full_a = [&](int s) { return bar_base + 8 * s; };
+    auto full_b = [&](int s) { return bar_base + 8 * (STAGES + s); };
+    auto empty = [&](int s) { return bar_base + 8 * (2 * STAGES + s); };
+    auto tmem_full = [&](int b) { return bar_base + 8 * (3 * STAGES + b); };
+    auto tmem_empty = [&](int b) { return bar_base + 8 * (3 * STAGES + 2 + b); };
+    volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(base_ptr + STAGES * Cfg::STAGE_BYTES + 8 * (3 * STAGES + 4));
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (warp == 8 && lane == 0) {
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(full_a(s), 8);          // the 8 producer warps
+            mbar_init(full_b(s), 1);
+            mbar_init(empty(s), 1);
+        }
+        for (int b = 0; b < 2; ++b) { mbar_init(tmem_full(b), 1); mbar_init(tmem_empty(b), 4); }
+        fence_barrier_init();
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_hi) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_lo) : "memory");
+    }
+    if (warp == 9) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+                     ::"r"(smem_u32((const void*)tmem_slot)), "n"(Cfg::TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_acc = *tmem_slot;
+
+    // work item -> (m tile, n tile, split); n fastest so neighbouring CTAs share the gathered A rows in L2
+    auto decode = [&](int w, int& mt, int& nt, int& sp) {
+        nt = w % wk.n_tiles; w /= wk.n_tiles;
+        mt = w % wk.m_tiles;
+        sp = w / wk.m_tiles;
+    };
+
+    if (warp < 8) {
+        // =============================== A producers ===============================
+        // All 8 warps fill every K-block (4 rows x one 16-byte chunk per thread) with a two-deep
+        // register prefetch: the global loads of K-blocks it+1 and it+2 are in flight while
+        // K-block it is transformed and stored.
+        const int chunk = threadIdx.x & 7;
+        const int r0 = threadIdx.x >> 3;                   // rows r0 + 32*j, j = 0..3
+        int git = 0;                                       // global K-block counter of this CTA
+        for (int w = blockIdx.x; w < wk.total; w += gridDim.x) {
+            int mt, nt, sp;
+            decode(w, mt, nt, sp);
+            const int m_base = mt * TC_BM;
+            const int kb_begin = sp * p.kb_per_split;
+            const int nkb = min(p.kblocks, kb_begin + p.kb_per_split) - kb_begin;
+            int rb[4], rsp[4], rc[4];
+            unsigned rvmask = 0;
+            const long long plane_sz = (long long)p.D * p.H * p.W;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                int m = m_base + r0 + 32 * j;
+                const bool v = m < p.M;
+                if (!v) m = 0;
+                const int xo = m % p.Wo; m /= p.Wo;
+                const int yo = m % p.Ho; m /= p.Ho;
+                const int zo = m % p.Do; m /= p.Do;
+                rb[j] = m;
+                const int z = zo * p.stride - p.pd, y = yo * p.stride - p.ph, x = xo * p.stride - p.pw;
+                rsp[j] = (z * p.H + y) * p.W + x;
+                rc[j] = ((z + 8) << 24) | ((y + 8) << 12) | (x + 8);
+                if (v) rvmask |= 1u << j;
+            }
+            int c0, kx, ky, kz;
+            {
+                const int k = kb_begin * TC_BK;
+                int tap = 0; c0 = k;
+                if (p.K != p.Cin) { tap = k / p.Cin; c0 = k - tap * p.Cin; }
+                kx = tap % p.kw; const int tq = tap / p.kw; ky = tq % p.kh; kz = tq / p.kh;
+            }
+            // prefetch ring of 3 K-blocks: slot q holds K-block (it % 3 == q)
+            float4 v[3][4];
+            unsigned okm[3]; int kc[3]; int ksp[3];
+            auto issue_loads = [&](int q) {
+                const int tap_sp = (kz * p.H + ky) * p.W + kx;
+                okm[q] = 0; kc[q] = c0; ksp[q] = tap_sp;
+                const float* xb = p.x + p.ico + chunk * 4 + c0;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int z = ((rc[j] >> 24) & 0xff) - 8 + kz, y = ((rc[j] >> 12) & 0xfff) - 8 + ky, x = (rc[j] & 0xfff) - 8 + kx;
+                    const bool inb = ((rvmask >> j) & 1u) && (unsigned)z < (unsigned)p.D && (unsigned)y < (unsigned)p.H &&
+                                     (unsigned)x < (unsigned)p.W;
+                    v[q][j] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (inb) {
+                        v[q][j] = __ldg(reinterpret_cast<const float4*>(xb + ((long long)rb[j] * plane_sz + rsp[j] + tap_sp) * p.ics));
+                        okm[q] |= 1u << j;
+                    }
+                }
+                c0 += TC_BK;
+                if (c0 == p.Cin) { c0 = 0; if (++kx == p.kw) { kx = 0; if (++ky == p.kh) { ky = 0; ++kz; } } }
+            };
+            auto process = [&](int q, int it) {
+                const int g_it = git + it;
+                const int s = g_it % STAGES;
+                const uint32_t n_use = g_it / STAGES;
+                if (p.pro != G6D_PRO_NONE) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        if (okm[q] & (1u << j)) {
+                            float4 sc, sh;
+                            if (p.pro == G6D_PRO_CORR) {
+                                sc = __ldg(reinterpret_cast<const float4*>(p.ps + (long long)(rsp[j] + ksp[q]) * p.Cin + kc[q] + chunk * 4));
+                                sh = __ldg(reinterpret_cast<const float4*>(p.pb + kc[q] + chunk * 4));
+                            } else {
+                                const long long g = rb[j] / (int)p.group_rows;       // 32-bit divide (host checks the range)
+                                sc = __ldg(reinterpret_cast<const float4*>(p.ps + g * p.Cin + kc[q] + chunk * 4));
+                                sh = __ldg(reinterpret_cast<const float4*>(p.pb + g * p.Cin + kc[q] + chunk * 4));
+                            }
+                            float4 x4 = v[q][j];
+                            x4.x = fmaf(x4.x, sc.x, sh.x); x4.y = fmaf(x4.y, sc.y, sh.y);
+                            x4.z = fmaf(x4.z, sc.z, sh.z); x4.w = fmaf(x4.w, sc.w, sh.w);
+                            if (p.pro == G6D_PRO_AFFINE_RELU) {
+                                x4.x = fmaxf(x4.x, 0.f); x4.y = fmaxf(x4.y, 0.f); x4.z = fmaxf(x4.z, 0.f); x4.w = fmaxf(x4.w, 0.f);
+                            }
+                            v[q][j] = x4;
+                        }
+                    }
+                }
+                mbar_wait(empty(s), (n_use & 1) ^ 1, 1, g_it);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const float4 x4 = v[q][j];
+                    float4 hi, lo;
+                    hi.x = __uint_as_float((__float_as_uint(x4.x) + 0x1000u) & 0xFFFFE000u);
+                    hi.y = __uint_as_float((__float_as_uint(x4.y) + 0x1000u) & 0xFFFFE000u);
+                    hi.z = __uint_as_float((__float_as_uint(x4.z) + 0x1000u) & 0xFFFFE000u);
+                    hi.w = __uint_as_float((__float_as_uint(x4.w) + 0x1000u) & 0xFFFFE000u);
+                    lo.x = x4.x - hi.x; lo.y = x4.y - hi.y; lo.z = x4.z - hi.z; lo.w = x4.w - hi.w;
+                    const int r = r0 + 32 * j;
+                    const uint32_t so = r * 128 + ((chunk ^ (r & 7)) << 4);
+                    asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(a_hi(s) + so), "f"(hi.x), "f"(hi.y), "f"(hi.z), "f"(hi.w) : "memory");
+                    asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(a_lo(s) + so), "f"(lo.x), "f"(lo.y), "f"(lo.z), "f"(lo.w) : "memory");
+                }
+                fence_proxy_async();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(full_a(s));
+            };
+            // software pipeline, unrolled by 3 so the ring slots are compile-time register names
+            if (nkb > 0) issue_loads(0);
+            if (nkb > 1) issue_loads(1);
+            for (int it = 0; it < nkb; it += 3) {
+                if (it + 2 < nkb) issue_loads(2);
+                process(0, it);
+                if (it + 1 < nkb) {
+                    if (it + 3 < nkb) issue_loads(0);
+                    process(1, it + 1);
+                }
+                if (it + 2 < nkb) {
+                    if (it + 4 < nkb) issue_loads(1);
+                    process(2, it + 2);
+                }
+            }
+            git += nkb;
+        }
+    } else if (warp == 8) {
+        // =============================== B producer (TMA) ===============================
+        if (lane == 0) {
+            int git = 0;
+            for (int w = blockIdx.x; w < wk.total; w += gridDim.x) {
+                int mt, nt, sp;
+                decode(w, mt, nt, sp);
+                const int kb_begin = sp * p.kb_per_split;
+                const int nkb = min(p.kblocks, kb_begin + p.kb_per_split) - kb_begin;
+                for (int it = 0; it < nkb; ++it, ++git) {
+                    const int s = git % STAGES;
+                    mbar_wait(empty(s), ((git / STAGES) & 1) ^ 1, 3, git);
+                    mbar_expect_tx(full_b(s), 2 * Cfg::B_BYTES);
+                    const int k = (kb_begin + it) * TC_BK;
+                    tma_load_2d(b_hi(s), &map_hi, full_b(s), k, nt * BN);
+                    tma_load_2d(b_lo(s), &map_lo, full_b(s), k, nt * BN);
+                }
+            }
+        }
+    } else if (warp == 9) {
+        // =============================== MMA issuer ===============================
+        if (lane == 0) {
+            const uint32_t idesc = umma_idesc_tf32(TC_BM, BN);
+            int git = 0, tile = 0;
+            for (int w = blockIdx.x; w < wk.total; w += gridDim.x, ++tile) {
+                int mt, nt, sp;
+                decode(w, mt, nt, sp);
+                const int kb_begin = sp * p.kb_per_split;
+                const int nkb = min(p.kblocks, kb_begin + p.kb_per_split) - kb_begin;
+                const int buf = tile & 1;
+                mbar_wait(tmem_empty(buf), ((tile >> 1) & 1) ^ 1, 6, tile);     // epilogue has drained this buffer
+                tc_fence_after();
+                const uint32_t acc0 = tmem_acc + (uint32_t)(buf * Cfg::BUF_COLS);
+                for (int it = 0; it < nkb; ++it, ++git) {
+                    const int s = git % STAGES;
+                    mbar_wait(full_a(s), (git / STAGES) & 1, 4, git);
+                    mbar_wait(full_b(s), (git / STAGES) & 1, 5, git);
+                    tc_fence_after();
+                    const uint64_t dah = umma_desc_sw128(a_hi(s)), dal = umma_desc_sw128(a_lo(s));
+                    const uint64_t dbh = umma_desc_sw128(b_hi(s)), dbl = umma_desc_sw128(b_lo(s));
+                    const uint32_t main_acc = acc0 + (uint32_t)((it % NMAIN) * BN);
+                    const uint32_t cross_acc = acc0 + (uint32_t)(NMAIN * BN);
+#pragma unroll
+                    for (int ks = 0; ks < TC_BK / 8; ++ks) {
+                        const uint64_t adv = (uint64_t)((ks * 32) >> 4);
+                        umma_tf32(cross_acc, dal + adv, dbh + adv, idesc, (it > 0 || ks > 0) ? 1u : 0u);
+                        umma_tf32(cross_acc, dah + adv, dbl + adv, idesc, 1u);
+                        umma_tf32(main_acc, dah + adv, dbh + adv, idesc, (it >= NMAIN || ks > 0) ? 1u : 0u);
+                    }
+                    umma_commit(empty(s));
+                }
+                umma_commit(tmem_full(buf));
+            }
+        }
+    } else {
+        // =============================== epilogue (warps 10-13) ===============================
+        const int quad = warp & 3;                     // TMEM lane quadrant = warp id % 4
+        int tile = 0;
+        for (int w = blockIdx.x; w < wk.total; w += gridDim.x, ++tile) {
+            int mt, nt, sp;
+            decode(w, mt, nt, sp);
+            const int kb_begin = sp * p.kb_per_split;
+            const int nkb = min(p.kblocks, kb_begin + p.kb_per_split) - kb_begin;
+            const int buf = tile & 1;
+            mbar_wait(tmem_full(buf), (tile >> 1) & 1, 2, tile);
+            tc_fence_after();
+            const int m = mt * TC_BM + quad * 32 + lane;
+            const int n_base = nt * BN;
+            const bool partial = p.splits > 1;
+            const int n_acc = nkb < NMAIN ? nkb : NMAIN;
+            const uint32_t tbase = tmem_acc + (uint32_t)(buf * Cfg::BUF_COLS) + ((uint32_t)(quad * 32) << 16);
+#pragma unroll 1
+            for (int cc = 0; cc < BN; cc += 16) {
+                float accv[16];
+#pragma unroll
+                for (int a = 0; a <= NMAIN; ++a) {
+                    const bool used = a == NMAIN || a < n_acc;
+                    uint32_t r[16];
+                    if (used) {
+                        asm volatile(
+                            "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                            : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                              "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+                            : "r"(tbase + (uint32_t)(a * BN + cc)));
+                        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) accv[j] = a == 0 ? __uint_as_float(r[j]) : accv[j] + __uint_as_float(r[j]);
+                    }
+                }
+                if (m < p.M) {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        const int n = n_base + cc + j;
+                        if (n < p.Cout) {
+                            float v = accv[j];
+                            if (partial) {
+                                p.ws[((long long)sp * p.M + m) * p.Cout + n] = v;
+                            } else {
+                                if (p.bias) v += __ldg(p.bias + n);
+                                p.y[(long long)m * p.ocs + p.oco + n] = tc_act(v, p.act);
+                            }
+                        }
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tmem_empty(buf));
+        }
+    }
+    __syncthreads();
+    if (warp == 9) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_acc), "n"(Cfg::TMEM_COLS) : "memory");
+    }
+}
+
 __global__ void conv_tc_reduce_kernel(const float* __restrict__ ws, const float* __restrict__ bias,
                                       float* __restrict__ y, int M, int Cout, int splits, int ocs, int oco, int act) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -445,6 +760,31 @@ static int launch_tc(const ConvTcP& p, const CUtensorMap& mh, const CUtensorMap&
     dim3 grid(ceil_div(p.M, TC_BM), ceil_div(p.Cout, BN), p.splits);
     conv_tc_kernel<BN><<<grid, TC_THREADS, Cfg::SMEM_BYTES, st>>>(p, mh, ml);
     G6D_CHECK_LAUNCH("g6d_conv_tc");
+    return G6D_OK;
+}
+
+static int tc_version() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("G6D_CONV_TC_V"); v = (e && e[0] == '1') ? 1 : 2; }
+    return v;
+}
+
+template <int BN>
+static int launch_tc2(const ConvTcP& p, const CUtensorMap& mh, const CUtensorMap& ml, cudaStream_t st) {
+    using Cfg = Tc2Cfg<BN>;
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(conv_tc2_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+        if (e != cudaSuccess) { set_error("g6d_conv_tc: cannot opt in to %d B of shared memory: %s", Cfg::SMEM_BYTES, cudaGetErrorString(e)); return G6D_ECUDA; }
+        configured = true;
+    }
+    Tc2Work wk;
+    wk.m_tiles = ceil_div(p.M, TC_BM); wk.n_tiles = ceil_div(p.Cout, BN);
+    const long long total = (long long)wk.m_tiles * wk.n_tiles * p.splits;
+    wk.total = (int)total;
+    const int grid = total < kNumSMs ? (int)total : kNumSMs;
+    conv_tc2_kernel<BN><<<grid, TC2_THREADS, Cfg::SMEM_BYTES, st>>>(p, wk, mh, ml);
+    G6D_CHECK_LAUNCH("g6d_conv_tc(v2)");
     return G6D_OK;
 }
 
@@ -897,10 +1237,19 @@ extern "C" int g6d_conv_tc(const g6d_conv_desc* desc, const float* x, const floa
     if ((rc = make_weight_map(&mh, w_hi, w_rows, p.K, bn)) != G6D_OK) return rc;
     if ((rc = make_weight_map(&ml, w_lo, w_rows, p.K, bn)) != G6D_OK) return rc;
     cudaStream_t st = as_stream(stream);
+    // v2 packs (z, y, x) + 8 into 8/12/12 bits and uses 32-bit spatial offsets and group indices
+    const bool v2_ok = p.D + p.pd + 8 < 256 && p.H + p.ph + 8 < 4096 && p.W + p.pw + 8 < 4096 &&
+                       (long long)p.D * p.H * p.W < (1ll << 30) && p.group_rows < (1ll << 31);
     if (bn == 256) rc = launch_tc<256>(p, mh, ml, st);
-    else if (bn == 128) rc = launch_tc<128>(p, mh, ml, st);
-    else if (bn == 64) rc = launch_tc<64>(p, mh, ml, st);
-    else rc = launch_tc<32>(p, mh, ml, st);
+    else if (tc_version() == 2 && v2_ok) {
+        if (bn == 128) rc = launch_tc2<128>(p, mh, ml, st);
+        else if (bn == 64) rc = launch_tc2<64>(p, mh, ml, st);
+        else rc = launch_tc2<32>(p, mh, ml, st);
+    } else {
+        if (bn == 128) rc = launch_tc<128>(p, mh, ml, st);
+        else if (bn == 64) rc = launch_tc<64>(p, mh, ml, st);
+        else rc = launch_tc<32>(p, mh, ml, st);
+    }
     if (rc != G6D_OK) return rc;
     if (p.splits > 1) {
         const long long n = (long long)p.M * p.Cout;
