@@ -319,6 +319,7 @@ def run_ours(args, rank, world, local_rank):
             'ffma_fallback': {'launches_per_step': ffma['n'] // 2, 'ms_per_step': ffma['ms'] / 2,
                               'tflops': ffma['work'] / max(ffma['ms'], 1e-9) / 1e9}}
     roof['frac'] = roof['achieved'] / roof['peak']
+    roof['frac_of_3xtf32_ceiling'] = roof['achieved'] / (roof['peak'] / 6.0)
     extra = []
     for key, label in (('g6d_sel_corr_score3', 'selector correlation + rotated-similarity score, 3 levels (S2)'),
                        ('g6d_ref_volume_fill', 'refiner unproject-and-aggregate volume fill (R2)')):

@@ -101,3 +101,36 @@ def test_selector_score_properties_at_scale():
         np.testing.assert_allclose(s3[l].cpu().numpy(), s1.cpu().numpy(), rtol=2e-6)
     s3b = ops.sel_corr_score3(refs, [q * 4.0 for q in qs])
     np.testing.assert_allclose(s3b.cpu().numpy(), 4.0 * s3.cpu().numpy(), rtol=1e-6)   # power-of-two scale: exact up to sum order
+
+
+def test_config4_angle_bins_36():
+    """BASELINE configs[3] per-shard shape in miniature: 36 rotation bins (angle_predict 515*36 wide)."""
+    c = cases.selector_case(seed=81, rfn=8, an=36)
+    net, sd = build('selector', c['cfg'])
+    net.load_ref_imgs(c['ref_imgs'], c['ref_poses'], c['object_center'], c['object_vert'])
+    feats, embed = O.sel_load_refs(sd, cases.u8_to_nchw(c['ref_imgs']), torch.from_numpy(c['ref_poses']),
+                                   torch.from_numpy(c['object_center']), torch.from_numpy(c['object_vert']))
+    logits, angles = O.sel_forward(sd, cases.u8_to_nchw(c['que_imgs']), feats, embed)
+    res = net.select_que_imgs(c['que_imgs'])
+    np.testing.assert_allclose(res['scores'], logits.numpy(), atol=4e-3)
+    top2 = torch.topk(logits, 2, 1)[0]
+    if float(top2[0, 0] - top2[0, 1]) > 2e-2:
+        assert res['ref_idx'].tolist() == torch.argmax(logits, 1).tolist()
+
+
+def test_config5_refiner_batch32_is_poses_independent():
+    """BASELINE configs[4] per-GPU batch (256 poses / 8 GPUs = 32): the batched forward must equal
+    its members run one at a time (per-sample InstanceNorm, no cross-pose term)."""
+    c = cases.refiner_case(seed=91, qn=32)
+    net, _ = build('refiner', {})
+    T = torch.from_numpy
+    data = {'que_imgs_info': {'imgs': cases.u8_to_nchw(c['que_imgs']).cuda(), 'Ks_in': T(c['que_Ks']).cuda(),
+                              'poses_in': T(c['que_poses']).cuda()},
+            'ref_imgs_info': {'imgs': cases.u8_to_nchw(c['ref_imgs']).cuda(), 'Ks': T(c['ref_Ks']).cuda(),
+                              'poses': T(c['ref_poses']).cuda()}, 'inference': True}
+    res = net(data)
+    for qi in (0, 17, 31):
+        one = {k: ({kk: vv[qi:qi + 1] for kk, vv in v.items()} if isinstance(v, dict) else v) for k, v in data.items()}
+        alone = net(one)
+        for key in ('rotation', 'offset', 'scale'):
+            np.testing.assert_allclose(alone[key].cpu().numpy(), res[key][qi:qi + 1].cpu().numpy(), atol=3e-5)
