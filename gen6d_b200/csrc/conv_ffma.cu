@@ -211,6 +211,59 @@ __global__ void conv_splitk_reduce_kernel(const float* __restrict__ ws, const fl
     y[m * ocs + oco + n] = act_apply(v, act);
 }
 
+// ------------------------------------------------------------------------------------------
+// First VGG layer: 3x3, Cin = 4 (RGB + a zero channel), Cout = 64, stride 1, pad 1.
+// K = 36 is far too small for the GEMM tiling (the layer is bound by its 64-channel output
+// write), so it gets a direct kernel: one thread per output pixel, 64 accumulators in registers,
+// the 36 x 64 weights broadcast from shared memory, 128-bit input loads, 16 x 128-bit stores.
+__global__ void __launch_bounds__(128) conv3x3_c4_o64_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                             const float* __restrict__ bias, float* __restrict__ y,
+                                                             int B, int H, int W, int act) {
+    __shared__ __align__(16) float ws[36 * 64];
+    __shared__ float bs[64];
+    for (int i = threadIdx.x; i < 36 * 64; i += blockDim.x) ws[i] = w[i];
+    if (threadIdx.x < 64) bs[threadIdx.x] = bias ? bias[threadIdx.x] : 0.f;
+    __syncthreads();
+    const long long m = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long M = (long long)B * H * W;
+    if (m >= M) return;
+    const int xo = (int)(m % W), yo = (int)((m / W) % H);
+    const long long b = m / ((long long)W * H);
+    float acc[64];
+#pragma unroll
+    for (int o = 0; o < 64; ++o) acc[o] = bs[o];
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky) {
+        const int yi = yo + ky - 1;
+        if ((unsigned)yi >= (unsigned)H) continue;
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx) {
+            const int xi = xo + kx - 1;
+            if ((unsigned)xi >= (unsigned)W) continue;
+            const float4 v = __ldg(reinterpret_cast<const float4*>(x + ((b * H + yi) * W + xi) * 4));
+            const float* wr = ws + (ky * 3 + kx) * 4 * 64;
+#pragma unroll
+            for (int o4 = 0; o4 < 16; ++o4) {
+                const float4 w0 = *reinterpret_cast<const float4*>(wr + o4 * 4);
+                const float4 w1 = *reinterpret_cast<const float4*>(wr + 64 + o4 * 4);
+                const float4 w2 = *reinterpret_cast<const float4*>(wr + 128 + o4 * 4);
+                const float4 w3 = *reinterpret_cast<const float4*>(wr + 192 + o4 * 4);   // 4th channel (zero for images)
+                acc[o4 * 4 + 0] = fmaf(v.x, w0.x, fmaf(v.y, w1.x, fmaf(v.z, w2.x, fmaf(v.w, w3.x, acc[o4 * 4 + 0]))));
+                acc[o4 * 4 + 1] = fmaf(v.x, w0.y, fmaf(v.y, w1.y, fmaf(v.z, w2.y, fmaf(v.w, w3.y, acc[o4 * 4 + 1]))));
+                acc[o4 * 4 + 2] = fmaf(v.x, w0.z, fmaf(v.y, w1.z, fmaf(v.z, w2.z, fmaf(v.w, w3.z, acc[o4 * 4 + 2]))));
+                acc[o4 * 4 + 3] = fmaf(v.x, w0.w, fmaf(v.y, w1.w, fmaf(v.z, w2.w, fmaf(v.w, w3.w, acc[o4 * 4 + 3]))));
+            }
+        }
+    }
+    float4* yr = reinterpret_cast<float4*>(y + m * 64);
+#pragma unroll
+    for (int o4 = 0; o4 < 16; ++o4) {
+        float4 r = make_float4(act_apply(acc[o4 * 4], act), act_apply(acc[o4 * 4 + 1], act), act_apply(acc[o4 * 4 + 2], act),
+                               act_apply(acc[o4 * 4 + 3], act));
+        __stcs(yr + o4, r);
+    }
+}
+
 static int fill_params(const g6d_conv_desc* d, ConvP& p) {
     G6D_REQUIRE(d != nullptr, "g6d_conv: null desc");
     G6D_REQUIRE(d->B > 0 && d->D > 0 && d->H > 0 && d->W > 0 && d->Cin > 0 && d->Cout > 0, "g6d_conv: bad dims");
@@ -271,6 +324,12 @@ extern "C" int g6d_conv(const g6d_conv_desc* desc, const float* x, const float* 
     if (p.splits > 1) G6D_REQUIRE(ws != nullptr, "g6d_conv: split-K workspace required (%d splits)", p.splits);
     p.x = x; p.w = w; p.bias = bias; p.ps = pro_scale; p.pb = pro_shift; p.y = y; p.ws = (float*)ws;
     cudaStream_t st = as_stream(stream);
+    if (p.Cin == 4 && p.ics == 4 && p.ico == 0 && p.Cout == 64 && p.ocs == 64 && p.oco == 0 && p.kd == 1 && p.kh == 3 &&
+        p.kw == 3 && p.stride == 1 && p.pd == 0 && p.ph == 1 && p.pw == 1 && p.D == 1 && p.pro == G6D_PRO_NONE) {
+        conv3x3_c4_o64_kernel<<<ceil_div(p.M, 128), 128, 0, st>>>(x, w, bias, y, p.B, p.H, p.W, p.act);
+        G6D_CHECK_LAUNCH("g6d_conv(first layer)");
+        return G6D_OK;
+    }
     const int bn = p.Cout > 64 ? 128 : (p.Cout > 32 ? 64 : 32);
     dim3 grid(ceil_div(p.M, BM), ceil_div(p.Cout, bn), p.splits);
     if (bn == 128) conv_ffma_kernel<8><<<grid, NT, 0, st>>>(p);
