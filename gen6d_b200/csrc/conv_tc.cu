@@ -346,6 +346,7 @@ conv_tc_kernel(const ConvTcP p, const __grid_constant__ CUtensorMap map_hi, cons
 //   * the smem ring never drains between tiles (one global K-block counter).
 // Warps: 0-7 A producers, 8 B producer (TMA), 9 MMA issuer + TMEM owner, 10-13 epilogue.
 constexpr int TC2_THREADS = 14 * 32;
+constexpr int TC2_PF = 12;          // weight-tile L2 prefetch distance (K-blocks)
 
 template <int BN> struct Tc2Cfg {
     static constexpr int A_BYTES = TC_BM * 128;
@@ -542,8 +543,19 @@ conv_tc2_kernel(const ConvTcP p, const Tc2Work wk, const __grid_constant__ CUten
                 decode(w, mt, nt, sp);
                 const int kb_begin = sp * p.kb_per_split;
                 const int nkb = min(p.kblocks, kb_begin + p.kb_per_split) - kb_begin;
+                // The weight tiles of a small-M layer are touched once and come from HBM: with only
+                // STAGES tiles in flight the ring is latency-bound (measured 5000 cycles per K-block
+                // at M = 660).  An L2 prefetch running TC2_PF K-blocks ahead costs no shared memory.
+                for (int it = 0; it < min(nkb, TC2_PF); ++it) {
+                    tma_prefetch_2d(&map_hi, (kb_begin + it) * TC_BK, nt * BN);
+                    tma_prefetch_2d(&map_lo, (kb_begin + it) * TC_BK, nt * BN);
+                }
                 for (int it = 0; it < nkb; ++it, ++git) {
                     const int s = git % STAGES;
+                    if (it + TC2_PF < nkb) {
+                        tma_prefetch_2d(&map_hi, (kb_begin + it + TC2_PF) * TC_BK, nt * BN);
+                        tma_prefetch_2d(&map_lo, (kb_begin + it + TC2_PF) * TC_BK, nt * BN);
+                    }
                     mbar_wait(empty(s), ((git / STAGES) & 1) ^ 1, 3, git);
                     mbar_expect_tx(full_b(s), 2 * Cfg::B_BYTES);
                     const int k = (kb_begin + it) * TC_BK;
@@ -732,7 +744,9 @@ static int fill_tc_params(const g6d_conv_desc* d, ConvTcP& p) {
     const long long ctas = (long long)ceil_div(M, TC_BM) * ceil_div(d->Cout, bn);
     int splits = 1;
     if (ctas < kNumSMs && p.kblocks >= 16) {
-        splits = (int)((kNumSMs + ctas - 1) / ctas);
+        // as many K splits as still fit in ONE wave of the 148 persistent CTAs (a second, partial wave
+        // of long items costs more than the parallelism it adds)
+        splits = (int)(kNumSMs / ctas);
         splits = splits > p.kblocks / 8 ? p.kblocks / 8 : splits;
         splits = splits < 1 ? 1 : splits;
     }
