@@ -32,7 +32,7 @@ import torch
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-E2E_WORKERS = int(os.environ.get('G6D_E2E_WORKERS', '4'))      # frames in flight per GPU (predict_many / device streams)
+E2E_WORKERS = int(os.environ.get('G6D_E2E_WORKERS', '6'))      # frames in flight per GPU (predict_many / device streams)
 METRIC = 'poses/sec end-to-end (128^2 crop, 64 refs, 3 refine iters)'
 WORKLOAD = ('full estimator detect->select->3x refine: synthetic 480x640 frame, detector 32 refs x 4 scales, '
             'selector 64 refs x 5 angles, refiner 6 views 32^3 volume, seeded random weights')
@@ -273,7 +273,8 @@ def run_ours(args, rank, world, local_rank):
         res = est.predict_many([imgs[i % len(imgs)] for i in range(n)], [K] * n, workers=E2E_WORKERS)
         out_poses.extend(r[0] for r in res)
 
-    pipelined(4)                                       # builds the worker clones, captures their graphs
+    pipelined(2 * E2E_WORKERS)                         # builds the worker clones, captures their graphs
+    pipelined(max(args.warmup, E2E_WORKERS))           # untimed warm-up of the whole pipelined path
     barrier()
     t0 = time.perf_counter()
     pipelined(args.steps)

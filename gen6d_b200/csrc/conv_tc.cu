@@ -614,6 +614,10 @@ conv_tc2_kernel(const ConvTcP p, const Tc2Work wk, const __grid_constant__ CUten
             const int m = mt * TC_BM + quad * 32 + lane;
             const int n_base = nt * BN;
             const bool partial = p.splits > 1;
+            // 128-bit stores need 16-byte aligned rows: channel strides / offsets multiples of 4 floats
+            const bool vec_ok = partial ? (p.Cout & 3) == 0
+                                        : ((p.ocs & 3) == 0 && (p.oco & 3) == 0 && (reinterpret_cast<uintptr_t>(p.y) & 15) == 0 &&
+                                           (!p.bias || (reinterpret_cast<uintptr_t>(p.bias) & 15) == 0));
             const int n_acc = nkb < NMAIN ? nkb : NMAIN;
             const uint32_t tbase = tmem_acc + (uint32_t)(buf * Cfg::BUF_COLS) + ((uint32_t)(quad * 32) << 16);
 #pragma unroll 1
@@ -635,16 +639,33 @@ conv_tc2_kernel(const ConvTcP p, const Tc2Work wk, const __grid_constant__ CUten
                     }
                 }
                 if (m < p.M) {
+                    const int n0 = n_base + cc;
+                    float* dst = partial ? p.ws + ((long long)sp * p.M + m) * p.Cout + n0
+                                         : p.y + (long long)m * p.ocs + p.oco + n0;
+                    const bool vec = vec_ok && n0 + 16 <= p.Cout;
+                    if (vec) {      // 4 x 128-bit stores per thread instead of 16 scalar ones
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) {
-                        const int n = n_base + cc + j;
-                        if (n < p.Cout) {
-                            float v = accv[j];
-                            if (partial) {
-                                p.ws[((long long)sp * p.M + m) * p.Cout + n] = v;
-                            } else {
-                                if (p.bias) v += __ldg(p.bias + n);
-                                p.y[(long long)m * p.ocs + p.oco + n] = tc_act(v, p.act);
+                        for (int j4 = 0; j4 < 4; ++j4) {
+                            float4 v = make_float4(accv[j4 * 4], accv[j4 * 4 + 1], accv[j4 * 4 + 2], accv[j4 * 4 + 3]);
+                            if (!partial) {
+                                if (p.bias) {
+                                    const float4 bb = __ldg(reinterpret_cast<const float4*>(p.bias + n0) + j4);
+                                    v.x += bb.x; v.y += bb.y; v.z += bb.z; v.w += bb.w;
+                                }
+                                v.x = tc_act(v.x, p.act); v.y = tc_act(v.y, p.act); v.z = tc_act(v.z, p.act); v.w = tc_act(v.w, p.act);
+                            }
+                            reinterpret_cast<float4*>(dst)[j4] = v;
+                        }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) {
+                            if (n0 + j < p.Cout) {
+                                float v = accv[j];
+                                if (!partial) {
+                                    if (p.bias) v += __ldg(p.bias + n0 + j);
+                                    v = tc_act(v, p.act);
+                                }
+                                dst[j] = v;
                             }
                         }
                     }
@@ -998,6 +1019,9 @@ conv_tcflat_kernel(const ConvFlatP p, const __grid_constant__ CUtensorMap map_hi
         constexpr int HALF = BN / 2;
         const int col0 = (warp >> 2) * HALF;
         const bool partial = p.splits > 1;
+        const bool vec_ok = partial ? (p.Cout & 3) == 0
+                                    : ((p.ocs & 3) == 0 && (p.oco & 3) == 0 && (reinterpret_cast<uintptr_t>(p.y) & 15) == 0 &&
+                                       (!p.bias || (reinterpret_cast<uintptr_t>(p.bias) & 15) == 0));
         const int total_mm = nunits * p.taps_per_seg;
         const int n_acc = total_mm < NMAIN ? total_mm : NMAIN;
 #pragma unroll
@@ -1020,16 +1044,31 @@ conv_tcflat_kernel(const ConvFlatP p, const __grid_constant__ CUtensorMap map_hi
                 }
             }
             if (valid) {
+                const int n0 = n_base + col0 + cc;
+                float* dst = partial ? p.ws + ((long long)split * p.M + m) * p.Cout + n0 : p.y + m * p.ocs + p.oco + n0;
+                if (vec_ok && n0 + 16 <= p.Cout) {
 #pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                    const int n = n_base + col0 + cc + j;
-                    if (n < p.Cout) {
-                        float v = accv[j];
-                        if (partial) {
-                            p.ws[((long long)split * p.M + m) * p.Cout + n] = v;
-                        } else {
-                            if (p.bias) v += __ldg(p.bias + n);
-                            p.y[m * p.ocs + p.oco + n] = tc_act(v, p.act);
+                    for (int j4 = 0; j4 < 4; ++j4) {
+                        float4 v = make_float4(accv[j4 * 4], accv[j4 * 4 + 1], accv[j4 * 4 + 2], accv[j4 * 4 + 3]);
+                        if (!partial) {
+                            if (p.bias) {
+                                const float4 bb = __ldg(reinterpret_cast<const float4*>(p.bias + n0) + j4);
+                                v.x += bb.x; v.y += bb.y; v.z += bb.z; v.w += bb.w;
+                            }
+                            v.x = tc_act(v.x, p.act); v.y = tc_act(v.y, p.act); v.z = tc_act(v.z, p.act); v.w = tc_act(v.w, p.act);
+                        }
+                        reinterpret_cast<float4*>(dst)[j4] = v;
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        if (n0 + j < p.Cout) {
+                            float v = accv[j];
+                            if (!partial) {
+                                if (p.bias) v += __ldg(p.bias + n0 + j);
+                                v = tc_act(v, p.act);
+                            }
+                            dst[j] = v;
                         }
                     }
                 }
