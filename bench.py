@@ -180,12 +180,15 @@ def run_ours(args, rank, world, local_rank):
     # ---- stage inputs for the device-resident measurement (captured from one real prediction)
     pose0, inter = est.predict(db.get_image(frames[0]), K)
     dev = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
-    frame_dev = dev(db.get_image(frames[0])[None])
-    crop_dev = dev(inter['det_que_img'][None])
+    frame_dev = dev(db.get_image(frames[0]))                     # uint8 [h,w,3], resident
+    _, M_crop = G.crop_similarity(None, inter['det_position'], 1 / inter['det_scale_r2q'], 0, 128)
+    crop_jobs = dev(G.pack_warp_jobs([frame_dev], [G.affine_dst_to_src(M_crop)]))
     probs = []
     for p in inter['refine_poses'][:3]:
-        pr = G.refine_problem(db, ids, db.get_image(frames[0]), K, p, 128, 6, True)
-        probs.append(tuple(dev(pr[k][None]) for k in ('que_img', 'que_K', 'que_pose', 'ref_imgs', 'ref_Ks', 'ref_poses')))
+        pr = G.refine_problem(db, ids, None, K, p, 128, 6, True, warp=False)
+        srcs = [frame_dev] + est.refiner._ref_images_dev(list(pr['ref_ids']))
+        mats = [G.perspective_dst_to_src(pr['que_H'])] + [G.perspective_dst_to_src(H) for H in pr['ref_Hs']]
+        probs.append((dev(G.pack_warp_jobs(srcs, mats)),) + tuple(dev(pr[k][None]) for k in ('que_K', 'que_pose', 'ref_Ks', 'ref_poses')))
     det, sel, rfr = est.detector, est.selector, est.refiner
 
     # W independent frames in flight, each on its own stream with its own captured stage graphs
@@ -201,10 +204,10 @@ def run_ours(args, rank, world, local_rank):
         d, sl, r = nets[0] if eager else nets[i % W]
         run = (lambda m, name, fn, a: fn(*a)) if eager else (lambda m, name, fn, a: m.stages.run(name, fn, a))
         with torch.no_grad():
-            run(d, 'detect', d._detect_u8, [frame_dev])
-            run(sl, 'select', sl._select_u8, [crop_dev])
+            run(d, 'detect', d._detect_u8, [frame_dev[None]])
+            run(sl, 'select_warp128', sl._select_warped(128), [crop_jobs])          # detection crop + selector
             for pr in probs:
-                run(r, 'refine', r._refine_u8, list(pr))
+                run(r, 'refine_warp128', r._refine_warped(128), list(pr))            # 7 look-at crops + refiner
 
     def device_steps(n):
         main = torch.cuda.current_stream()
@@ -343,7 +346,7 @@ def run_ours(args, rank, world, local_rank):
             'e2e': {'value': world * args.steps / (pipe_ms * 1e-3), 'unit': 'poses/s', 'ms_per_step': pipe_ms / args.steps,
                     'h2d_bytes_per_step': io['h2d'] // n_calls, 'd2h_bytes_per_step': io['d2h'] // n_calls,
                     'api': f'Gen6DEstimator.predict_many(numpy frames, Ks, workers={E2E_WORKERS}) -> numpy poses: per frame the same '
-                           'predict() (pinned H2D of the frame / crops, OpenCV warps on the host, D2H of every stage '
+                           'predict() (pinned H2D of the frame once, crops cut from it on the device, camera geometry on the host, D2H of every stage '
                            f'result), {E2E_WORKERS} frames in flight per GPU',
                     'single_frame_latency': {'value': e2e_v, 'unit': 'poses/s', 'ms_per_step': e2e_wall_ms / args.steps,
                                              'api': 'Gen6DEstimator.predict(numpy frame, K), one frame at a time'}},

@@ -34,6 +34,8 @@ P, I, L, F = C.c_void_p, C.c_int, C.c_longlong, C.c_float
 _SIGNATURES = {
     'g6d_preprocess_u8': [P, P, L, I, I, P],
     'g6d_imagenet_norm': [P, P, L, I, I, P],
+    'g6d_warp_perspective_u8': [P, I, P, I, I, P],
+    'g6d_warp_affine_u8': [P, I, P, I, I, P],
     'g6d_nchw_to_nhwc': [P, P, I, I, I, I, I, P],
     'g6d_nhwc_to_nchw': [P, P, I, I, I, I, I, P],
     'g6d_resize_bilinear': [P, P, I, I, I, I, I, I, I, I, P],

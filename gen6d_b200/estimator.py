@@ -23,6 +23,7 @@ class Gen6DEstimator:
         'detector': None,
         'refiner': None,
         'refine_iter': 3,
+        'host_warps': False,      # True: keep the between-stage crops on the host in OpenCV, as the reference does
         'host_threads': None,     # OpenCV / torch-CPU threads for the host geometry (None: min(8, usable CPUs))
     }
 
@@ -78,12 +79,22 @@ class Gen6DEstimator:
     def predict(self, que_img, que_K, pose_init=None):
         """estimator.py:173-216.  que_img uint8 [h,w,3], que_K [3,3] -> (pose [3,4], inter_results)."""
         inter = {}
+        res = self.cfg['ref_resolution']
+        host_warps = self.cfg['host_warps']
+        # the frame goes to the device once; the detection crop and the refinement look-at crops are
+        # cut from it there (bit-exact with the OpenCV warps the reference runs on the host)
+        frame = None if host_warps else self.detector.upload_frame(que_img)
         if pose_init is None:
-            det = self.detector.detect_que_imgs(que_img[None])
+            det = self.detector.detect_que_imgs(que_img[None], que_dev=None if host_warps else frame[None])
             position, scale_r2q = det['positions'][0], det['scales'][0]
-            crop, _ = G.crop_similarity(que_img, position, 1 / scale_r2q, 0, self.cfg['ref_resolution'])
+            if host_warps:
+                crop, _ = G.crop_similarity(que_img, position, 1 / scale_r2q, 0, res)
+                sel = self.selector.select_que_imgs(crop[None])
+            else:
+                _, M = G.crop_similarity(None, position, 1 / scale_r2q, 0, res)
+                sel = self.selector.select_from_frame(frame, M, res)
+                crop = sel['que_imgs'][0]
             inter.update(det_position=position, det_scale_r2q=scale_r2q, det_que_img=crop)
-            sel = self.selector.select_que_imgs(crop[None])
             ref_idx, angle_r2q, scores = sel['ref_idx'][0], sel['angles'][0], sel['scores'][0]
             inter.update(sel_angle_r2q=angle_r2q, sel_scores=scores, sel_ref_idx=ref_idx)
             pose = G.pose_from_similarity(position, scale_r2q, angle_r2q, self.ref_info['poses'][ref_idx],
@@ -93,7 +104,8 @@ class Gen6DEstimator:
         if self.refiner is not None:
             poses = [pose]
             for _ in range(self.cfg['refine_iter']):
-                pose = self.refiner.refine_que_imgs(que_img, que_K, pose, size=128, ref_num=6, ref_even=True)
+                pose = self.refiner.refine_que_imgs(que_img, que_K, pose, size=128, ref_num=6, ref_even=True,
+                                                    que_dev=frame, host_warps=host_warps)
                 poses.append(pose)
             inter['refine_poses'] = poses
         return pose, inter

@@ -144,7 +144,8 @@ def similarity_2d(position, scale, angle, target):
 
 
 def crop_similarity(img, position, scale, angle, size):
-    """base_utils.py:646-655 transformation_crop (float32 2x3 matrix, cv2.warpAffine)."""
+    """base_utils.py:646-655 transformation_crop (float32 2x3 matrix, cv2.warpAffine).  img=None:
+    only the matrix (the caller warps on the device with g6d_warp_affine_u8)."""
     # the reference accumulates the 2x3 blocks in float32; keep the same rounding
     M = np.asarray([[1, 0, -position[0]], [0, 1, -position[1]]], np.float32)
     S = np.asarray([[scale, 0, 0], [0, scale, 0]], np.float32)
@@ -152,7 +153,42 @@ def crop_similarity(img, position, scale, angle, size):
     T = np.asarray([[1, 0, size / 2], [0, 1, size / 2]], np.float32)
     for nxt in (S, Rm, T):
         M = np.concatenate([nxt[:, :2] @ M[:, :2], (nxt[:, :2] @ M[:, 2] + nxt[:, 2])[:, None]], 1)
-    return cv2.warpAffine(img, M, (size, size), flags=cv2.INTER_LINEAR), M
+    return (cv2.warpAffine(img, M, (size, size), flags=cv2.INTER_LINEAR) if img is not None else None), M
+
+
+# ------------------------------------------------------------------------------------------ device warps
+WARP_JOB = np.dtype([('src', '<u8'), ('rows', '<i4'), ('cols', '<i4'), ('M', '<f8', (9,))])   # g6d_warp_job
+
+
+def perspective_dst_to_src(H):
+    """The matrix cv2.warpPerspective actually iterates with: cv::invert (LU) of H taken to double."""
+    ok, inv = cv2.invert(np.ascontiguousarray(H, dtype=np.float64))
+    return inv.reshape(9)
+
+
+def affine_dst_to_src(M):
+    """The 2x3 matrix cv2.warpAffine iterates with: OpenCV's closed-form inverse, evaluated in
+    double in OpenCV's operation order (so that the fixed-point coordinates round identically)."""
+    m = [float(v) for v in np.asarray(M, np.float64).reshape(6)]
+    d = m[0] * m[4] - m[1] * m[3]
+    d = 1.0 / d if d != 0 else 0.0
+    a11, a22 = m[4] * d, m[0] * d
+    m[0], m[1], m[3], m[4] = a11, m[1] * -d, m[3] * -d, a22
+    b1 = -m[0] * m[2] - m[1] * m[5]
+    b2 = -m[3] * m[2] - m[4] * m[5]
+    m[2], m[5] = b1, b2
+    return np.asarray(m + [0.0, 0.0, 1.0])
+
+
+def pack_warp_jobs(srcs, mats):
+    """srcs: device uint8 tensors [rows, cols, 3] (contiguous); mats: dst->src matrices [9].
+    -> uint8 [n*88] host array, the g6d_warp_job records of include/gen6d_b200.h."""
+    jobs = np.zeros(len(srcs), WARP_JOB)
+    for j, (t, m) in enumerate(zip(srcs, mats)):
+        if t.dim() != 3 or t.shape[2] != 3 or not t.is_contiguous() or not t.is_cuda or t.element_size() != 1:
+            raise ValueError('pack_warp_jobs: sources must be contiguous CUDA uint8 [rows, cols, 3] tensors')
+        jobs[j] = (t.data_ptr(), t.shape[0], t.shape[1], m)
+    return jobs.view(np.uint8)
 
 
 # ------------------------------------------------------------------------------------------ view selection
@@ -218,7 +254,7 @@ def _project_center_batch(center, poses, Ks):
     return p[:, :2] / d[:, None]
 
 
-def normalize_reference_views(database, ids, size, margin, align_pose=None, align_K=None):
+def normalize_reference_views(database, ids, size, margin, align_pose=None, align_K=None, warp=True):
     """database_utils.py:54-110 (rectify_rot=True, no extra rotations): every reference view is
     re-rendered as a look-at crop of the object at a common apparent size, with the in-plane
     orientation either 'object-up' (build time) or aligned to a given pose (refinement).
@@ -257,7 +293,7 @@ def normalize_reference_views(database, ids, size, margin, align_pose=None, alig
     rect = R.astype(np.float32)
     poses_new = np.concatenate([rect @ poses[:, :, :3], rect @ poses[:, :, 3:]], 2)
     imgs = np.stack([cv2.warpPerspective(database.get_image(i), Hs[k], (size, size), flags=cv2.INTER_LINEAR)
-                     for k, i in enumerate(ids)], 0)
+                     for k, i in enumerate(ids)], 0) if warp else None   # warp=False: the caller warps on the device
     return imgs, K_new, poses_new, Hs
 
 
@@ -348,10 +384,12 @@ def _normalized_view(database):
     return _VIEW_CACHE[key]
 
 
-def refine_problem(database, ref_ids, que_img, que_K, in_pose, size=128, ref_num=6, ref_even=False, margin=0.05):
+def refine_problem(database, ref_ids, que_img, que_K, in_pose, size=128, ref_num=6, ref_even=False, margin=0.05,
+                   warp=True):
     """Everything refiner.py:285-325 prepares on the host for one refinement step: the query
     look-at crop at the input pose and the `ref_num` nearest reference views re-rendered with
-    their in-plane orientation aligned to it."""
+    their in-plane orientation aligned to it.  warp=False skips the OpenCV warps (que_img may be
+    None) and only returns their homographies 'que_H' / 'ref_Hs' for g6d_warp_perspective_u8."""
     view = _normalized_view(database)
     pose_n = view.normalize_pose(in_pose)
     center = view.object_center()
@@ -359,10 +397,11 @@ def refine_problem(database, ref_ids, que_img, que_K, in_pose, size=128, ref_num
     dist = np.linalg.norm(camera_center(pose_n) - center)
     scale = size * (1 - margin) / view.object_diameter() * dist / f_look
     cen_px = project(center[None].astype(np.float64), pose_n, que_K)[0][0]
-    que_crop, K_warp, pose_warp, pose_rect, _ = look_at_crop(que_img, que_K, pose_n, cen_px, 0, scale, size, size)
+    que_crop, K_warp, pose_warp, pose_rect, que_H = look_at_crop(que_img if warp else None, que_K, pose_n, cen_px, 0,
+                                                                 scale, size, size)
     ids = select_views_near_pose(view, center, ref_ids, pose_warp, ref_num, ref_even, min(128, len(ref_ids)))
-    ref_imgs, ref_Ks, ref_poses, _ = normalize_reference_views(view, ids, size, margin, pose_warp, K_warp)
-    return {'view': view, 'que_img': que_crop, 'que_K': K_warp.astype(np.float32),
+    ref_imgs, ref_Ks, ref_poses, ref_Hs = normalize_reference_views(view, ids, size, margin, pose_warp, K_warp, warp)
+    return {'view': view, 'que_img': que_crop, 'que_K': K_warp.astype(np.float32), 'que_H': que_H, 'ref_Hs': ref_Hs,
             'que_pose': pose_warp.astype(np.float32), 'pose_rect': pose_rect, 'center': center, 'ref_ids': ids,
             'ref_imgs': ref_imgs, 'ref_Ks': ref_Ks.astype(np.float32), 'ref_poses': ref_poses.astype(np.float32)}
 

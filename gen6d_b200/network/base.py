@@ -73,6 +73,11 @@ class PackedModule(nn.Module):
         IO_BYTES['h2d'] += t.numel() * t.element_size()
         return slot.to(self.device, non_blocking=True)
 
+    def upload_frame(self, que_img):
+        """uint8 [h,w,3] query frame -> device, once per frame: the detector reads it, the detection
+        crop and every refinement iteration's look-at crop are cut from it on the device."""
+        return self._to_dev(que_img)
+
     @staticmethod
     def _to_host(t):
         """device -> numpy (synchronising D2H read of a result)."""

@@ -153,9 +153,10 @@ class Detector(PackedModule):
             u8 = self._to_dev(ref_imgs)
             self._load_nhwc(ops.preprocess_u8(u8, out_c=3, imagenet_norm=False))
 
-    def detect_que_imgs(self, que_imgs):
-        """@param que_imgs: uint8 [qn,h,w,3] -> {'positions': f32 [qn,2], 'scales': f32 [qn]} (detector.py:291-304)"""
+    def detect_que_imgs(self, que_imgs, que_dev=None):
+        """@param que_imgs: uint8 [qn,h,w,3] -> {'positions': f32 [qn,2], 'scales': f32 [qn]} (detector.py:291-304)
+        que_dev: the same frames already on the device (upload_frame), to skip the upload."""
         with torch.no_grad():
-            out = self.stages.run('detect', self._detect_u8, [self._to_dev(que_imgs)])
+            out = self.stages.run('detect', self._detect_u8, [self._to_dev(que_imgs) if que_dev is None else que_dev])
             out = self._to_host(out)
         return {'positions': out[:, :2].copy(), 'scales': out[:, 2].copy()}

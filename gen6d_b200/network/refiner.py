@@ -6,6 +6,8 @@ Everything is batched over the qn poses of a call: the 2-D feature net runs once
 qn*(rfn+1) images, the volume fill on all qn volumes, the 3-D conv stack on [qn, 32,32,32, C];
 InstanceNorm groups are per image / per pose, exactly as in the reference (no cross-pose term).
 """
+import threading
+
 import numpy as np
 import torch
 
@@ -15,6 +17,7 @@ from .base import Branches, PackedModule, linear_as_conv
 from .params import RefineFeatureParams, RefineRegressorParams, RefineVolumeParams
 
 IN_EPS = 1e-5
+_UPLOAD_LOCK = threading.Lock()
 
 
 class VolumeRefiner(PackedModule):
@@ -28,6 +31,7 @@ class VolumeRefiner(PackedModule):
         self.regressor = RefineRegressorParams()
         self.ref_database = None
         self.ref_ids = None
+        self._ref_dev = {}
 
     # ------------------------------------------------------------------ weights
     def _pack(self):
@@ -174,12 +178,49 @@ class VolumeRefiner(PackedModule):
     def load_ref_imgs(self, ref_database, ref_ids):
         self.ref_database = ref_database
         self.ref_ids = ref_ids
+        self._ref_dev = {}          # image id -> device uint8 [rows, cols, 3] (filled on first use)
 
-    def refine_que_imgs(self, que_img, que_K, in_pose, size=128, ref_num=6, ref_even=False):
-        """Host wrapper of refiner.py:275-341 (same arguments and result: pose [3,4] float32)."""
+    def _ref_images_dev(self, ids):
+        """The database images the look-at crops are cut from, resident on the device: all of them
+        are uploaded on first use (once per object) and then shared read-only by every worker
+        clone / stream, hence the lock and the synchronise before anyone else may see them."""
+        if not self._ref_dev:
+            with _UPLOAD_LOCK:
+                if not self._ref_dev:
+                    dev = {i: torch.from_numpy(np.ascontiguousarray(self.ref_database.get_image(i))).to(self.device)
+                           for i in self.ref_ids}
+                    torch.cuda.current_stream().synchronize()
+                    self._ref_dev.update(dev)
+        return [self._ref_dev[i] for i in ids]
+
+    def _refine_warped(self, size):
+        def fn(jobs, que_K, que_pose, ref_Ks, ref_poses):
+            n = jobs.numel() // ops.WARP_JOB_BYTES
+            crops = ops.warp_perspective_u8(jobs, n, size, size)
+            return self._refine_u8(crops[:1], que_K, que_pose, crops[1:][None], ref_Ks, ref_poses)
+        return fn
+
+    def refine_que_imgs(self, que_img, que_K, in_pose, size=128, ref_num=6, ref_even=False, que_dev=None,
+                        host_warps=False):
+        """Host wrapper of refiner.py:275-341 (same arguments and result: pose [3,4] float32).
+        The look-at crops of the query frame and of the selected reference views are cut on the
+        device by g6d_warp_perspective_u8 (bit-exact with cv2.warpPerspective, so the result is the
+        same as with host_warps=True, which keeps OpenCV on the host as the reference does).
+        que_dev: the frame already on the device (upload_frame), to share it across iterations."""
         from .. import geometry as G
-        prob = G.refine_problem(self.ref_database, self.ref_ids, que_img, que_K, in_pose, size, ref_num, ref_even)
+        prob = G.refine_problem(self.ref_database, self.ref_ids, que_img, que_K, in_pose, size, ref_num, ref_even,
+                                warp=host_warps)
+        cams = ('que_K', 'que_pose', 'ref_Ks', 'ref_poses')
         with torch.no_grad():
-            args = [self._to_dev(prob[k][None]) for k in ('que_img', 'que_K', 'que_pose', 'ref_imgs', 'ref_Ks', 'ref_poses')]
-            out = self._to_host(self.stages.run('refine', self._refine_u8, args))[0]
+            if host_warps:
+                args = [self._to_dev(prob[k][None]) for k in ('que_img', 'que_K', 'que_pose', 'ref_imgs', 'ref_Ks', 'ref_poses')]
+                out = self.stages.run('refine', self._refine_u8, args)
+            else:
+                if que_dev is None:
+                    que_dev = self.upload_frame(que_img)
+                srcs = [que_dev] + self._ref_images_dev(list(prob['ref_ids']))
+                mats = [G.perspective_dst_to_src(prob['que_H'])] + [G.perspective_dst_to_src(H) for H in prob['ref_Hs']]
+                args = [self._to_dev(G.pack_warp_jobs(srcs, mats))] + [self._to_dev(prob[k][None]) for k in cams]
+                out = self.stages.run(f'refine_warp{size}', self._refine_warped(size), args)
+            out = self._to_host(out)[0]
         return G.apply_refinement(prob, quat=out[:4], offset=out[4:6], scale=2.0 ** out[6])

@@ -279,6 +279,28 @@ class ViewpointSelector(PackedModule):
             self._load_nhwc(x, rfn, an, ref_poses.astype(np.float32), object_center.astype(np.float32),
                             object_vert.astype(np.float32))
 
+    def _select_warped(self, size):
+        def fn(jobs):
+            crop = ops.warp_affine_u8(jobs, jobs.numel() // ops.WARP_JOB_BYTES, size, size)
+            return (crop,) + tuple(self._select_u8(crop))
+        return fn
+
+    def select_from_frame(self, frame_dev, M, size):
+        """estimator.py:184-186 in one device stage: cut the detection crop out of the frame with the
+        2x3 similarity M (g6d_warp_affine_u8, bit-exact with the reference's cv2.warpAffine), then
+        select_que_imgs on it.  frame_dev: uint8 [h,w,3] on the device.  Returns the select_que_imgs
+        dict plus 'que_imgs' (the crop, uint8 [1,size,size,3], as the reference hands it on)."""
+        from .. import geometry as G
+        fn = self._select_warped(size)
+        with torch.no_grad():
+            jobs = self._to_dev(G.pack_warp_jobs([frame_dev], [G.affine_dst_to_src(M)]))
+            if self.comm.world == 1:
+                crop, idx, out, logits = self.stages.run(f'select_warp{size}', fn, [jobs])
+            else:
+                crop, idx, out, logits = fn(jobs)           # collectives inside: run eagerly
+            crop, idx, out, logits = [self._to_host(t) for t in (crop, idx, out, logits)]
+        return {'ref_idx': idx, 'angles': out[:, 0].copy(), 'scores': logits, 'que_imgs': crop}
+
     def select_que_imgs(self, que_imgs):
         """@param que_imgs: uint8 [qn,h,w,3] -> {'ref_idx': i64 [qn], 'angles': f32 [qn], 'scores': f32 [qn,rfn]}
         (selector.py:165-175; the angle is returned un-rescaled, as the reference does)"""

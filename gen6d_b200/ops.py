@@ -15,6 +15,9 @@ from . import _lib
 from ._lib import ACT_LEAKY01, ACT_NONE, ACT_RELU, PRO_AFFINE, PRO_AFFINE_RELU, PRO_CORR, PRO_NONE  # noqa: F401
 
 
+WARP_JOB_BYTES = 88   # sizeof(g6d_warp_job)
+
+
 def _stream():
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
@@ -75,6 +78,25 @@ def preprocess_u8(img, out_c=4, imagenet_norm=True):
     out = torch.empty(*img.shape[:-1], out_c, device=img.device, dtype=torch.float32)
     _call('g6d_preprocess_u8', _p(img, torch.uint8), _p(out), img.numel() // 3, out_c, int(imagenet_norm), _stream())
     return out
+
+
+def _warp(name, jobs, n_jobs, h, w):
+    if jobs.dtype != torch.uint8 or jobs.numel() != n_jobs * WARP_JOB_BYTES:
+        raise ValueError(f'{name}: jobs must be the packed bytes of {n_jobs} g6d_warp_job records')
+    out = torch.empty(n_jobs, h, w, 3, device=jobs.device, dtype=torch.uint8)
+    _call(name, _p(jobs, torch.uint8), n_jobs, _p(out, torch.uint8), h, w, _stream())
+    return out
+
+
+def warp_perspective_u8(jobs, n_jobs, h, w):
+    """cv2.warpPerspective (u8, INTER_LINEAR, zero border), bit-exact, for n_jobs (image, H) pairs.
+    jobs: device uint8 tensor holding n_jobs packed g6d_warp_job records (geometry.pack_warp_jobs)."""
+    return _warp('g6d_warp_perspective_u8', jobs, n_jobs, h, w)
+
+
+def warp_affine_u8(jobs, n_jobs, h, w):
+    """cv2.warpAffine counterpart of warp_perspective_u8."""
+    return _warp('g6d_warp_affine_u8', jobs, n_jobs, h, w)
 
 
 def imagenet_norm(x, out_c=4):

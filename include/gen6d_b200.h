@@ -48,6 +48,22 @@ long long g6d_launch_count(void);
  * out_c = 3 or 4 (channel 3 = 0: padding so the first VGG conv can use 128-bit loads). */
 int g6d_preprocess_u8(const uint8_t* img, float* out, long long n_pixels, int out_c, int imagenet_norm,
                       g6d_stream_t stream);
+/* One image warp: `src` is a device uint8 [rows, cols, 3] image; M is the row-major DST -> SRC map
+ * (what OpenCV holds after its internal inversion: cv::invert of the 3x3 for warpPerspective; the
+ * closed-form 2x3 inverse, rows M[0..2] and M[3..5], for warpAffine - M[6..8] unused there). */
+typedef struct g6d_warp_job {
+    const uint8_t* src;
+    int rows, cols;
+    double M[9];
+} g6d_warp_job;
+/* cv2.warpPerspective(src, H, (w, h), flags=INTER_LINEAR) with a zero constant border, bit-exact with
+ * OpenCV's 8-bit fixed-point path, for n_jobs (image, matrix) pairs at once: the look-at crops of
+ * network/refiner.py:285-325 (utils/database_utils.py:8-25 look_at_crop, :54-110
+ * normalize_reference_views).  jobs: DEVICE array [n_jobs]; out u8 [n_jobs, h, w, 3]. */
+int g6d_warp_perspective_u8(const g6d_warp_job* jobs, int n_jobs, uint8_t* out, int h, int w, g6d_stream_t stream);
+/* cv2.warpAffine(src, M, (w, h), flags=INTER_LINEAR), same conventions: the detection crop of
+ * estimator.py:184 (utils/base_utils.py:646-655 transformation_crop). */
+int g6d_warp_affine_u8(const g6d_warp_job* jobs, int n_jobs, uint8_t* out, int h, int w, g6d_stream_t stream);
 /* (x - mean) / std on f32 [n_pixels, in_c] -> [n_pixels, out_c] (in_c, out_c in {3,4})
  * (network/detector.py:189, selector.py:115, refiner.py:65) */
 int g6d_imagenet_norm(const float* in, float* out, long long n_pixels, int in_c, int out_c, g6d_stream_t stream);

@@ -15,22 +15,25 @@ def T(fn, n=10):
     torch.cuda.synchronize(); return (time.perf_counter() - t) / n * 1e3
 pose, inter = est.predict(img, K)
 print('predict ms', T(lambda: est.predict(img, K)))
-print(' detect_que_imgs ms', T(lambda: est.detector.detect_que_imgs(img[None])))
-crop = inter['det_que_img']
-print(' crop_similarity ms', T(lambda: G.crop_similarity(img, inter['det_position'], 1 / inter['det_scale_r2q'], 0, 128)))
-print(' select_que_imgs ms', T(lambda: est.selector.select_que_imgs(crop[None])))
+est.cfg['host_warps'] = True
+print('predict ms (host warps, as the reference)', T(lambda: est.predict(img, K)))
+est.cfg['host_warps'] = False
+frame = est.detector.upload_frame(img)
+print(' upload_frame ms', T(lambda: est.detector.upload_frame(img)))
+print(' detect_que_imgs ms', T(lambda: est.detector.detect_que_imgs(img[None], que_dev=frame[None])))
+_, M = G.crop_similarity(None, inter['det_position'], 1 / inter['det_scale_r2q'], 0, 128)
+print(' select_from_frame ms', T(lambda: est.selector.select_from_frame(frame, M, 128)))
 p0 = inter['refine_poses'][0]
-print(' refine_que_imgs ms', T(lambda: est.refiner.refine_que_imgs(img, K, p0, 128, 6, True)))
-print('   refine_problem ms', T(lambda: G.refine_problem(db, ids, img, K, p0, 128, 6, True)))
-prob = G.refine_problem(db, ids, img, K, p0, 128, 6, True)
-args = [est.refiner._to_dev(prob[k][None]) for k in ('que_img', 'que_K', 'que_pose', 'ref_imgs', 'ref_Ks', 'ref_poses')]
-print('   _to_dev x6 ms', T(lambda: [est.refiner._to_dev(prob[k][None]) for k in ('que_img', 'que_K', 'que_pose', 'ref_imgs', 'ref_Ks', 'ref_poses')]))
-print('   refine graph ms', T(lambda: est.refiner.stages.run('refine', est.refiner._refine_u8, args)))
-print('   refine eager ms', T(lambda: est.refiner._refine_u8(*args)))
-print('   apply_refinement ms', T(lambda: G.apply_refinement(prob, np.array([1., 0, 0, 0]), np.array([0.1, 0.1]), 1.01)))
-u8 = est.detector._to_dev(img[None])
-print(' detect graph ms', T(lambda: est.detector.stages.run('detect', est.detector._detect_u8, [u8])))
-print(' detect eager ms', T(lambda: est.detector._detect_u8(u8)))
-c8 = est.selector._to_dev(crop[None])
-print(' select graph ms', T(lambda: est.selector.stages.run('select', est.selector._select_u8, [c8])))
-print(' select eager ms', T(lambda: est.selector._select_u8(c8)))
+print(' refine_que_imgs ms (device warps)', T(lambda: est.refiner.refine_que_imgs(img, K, p0, 128, 6, True, que_dev=frame)))
+print(' refine_que_imgs ms (host warps)', T(lambda: est.refiner.refine_que_imgs(img, K, p0, 128, 6, True, host_warps=True)))
+print('   refine_problem ms (host warps)', T(lambda: G.refine_problem(db, ids, img, K, p0, 128, 6, True)))
+print('   refine_problem ms (no warps)', T(lambda: G.refine_problem(db, ids, None, K, p0, 128, 6, True, warp=False)))
+pr = G.refine_problem(db, ids, None, K, p0, 128, 6, True, warp=False)
+def jobs():
+    srcs = [frame] + est.refiner._ref_images_dev(list(pr['ref_ids']))
+    mats = [G.perspective_dst_to_src(pr['que_H'])] + [G.perspective_dst_to_src(H) for H in pr['ref_Hs']]
+    return G.pack_warp_jobs(srcs, mats)
+print('   pack_warp_jobs ms', T(jobs))
+args = [est.refiner._to_dev(jobs())] + [est.refiner._to_dev(pr[k][None]) for k in ('que_K', 'que_pose', 'ref_Ks', 'ref_poses')]
+print('   refine graph ms', T(lambda: est.refiner.stages.run('refine_warp128', est.refiner._refine_warped(128), args)))
+print('   apply_refinement ms', T(lambda: G.apply_refinement(pr, np.array([1., 0, 0, 0]), np.array([0.1, 0.1]), 1.01)))
