@@ -683,6 +683,384 @@ conv_tc2_kernel(const ConvTcP p, const Tc2Work wk, const __grid_constant__ CUten
     }
 }
 
+// ==========================================================================================
+// conv_tc3_kernel: conv_tc2_kernel with the A operand in TENSOR MEMORY.
+//
+// Measured with tools/probes/mma_rate.cu on B200: a kind::tf32 M=128 MMA takes max(N/2, 32 + N/4)
+// cycles when A comes from shared memory (the 4 KB A slice is re-read at 128 B/clk for every one of
+// the three split terms) but N/2 cycles - the tensor floor - when A is in TMEM.  In the 3xTF32 scheme
+// the shared-memory traffic of v2 (A stores + A re-reads x3 + B) is 160 KB per K-block at N = 128,
+// i.e. ~1250 cycles against 768 cycles of tensor time; here the producers write their tf32 hi/lo
+// halves straight from registers into TMEM with tcgen05.st and the MMAs are issued in the
+// [D], [A], B-descriptor form, so shared memory only carries the TMA-fed weight tiles.
+//   * producers: thread = one tile row (TMEM lane = 32*(warp%4) + lane), warp/4 = which 16 of the
+//     K-block's 32 channels; 64 contiguous bytes per thread per K-block, two-deep register prefetch;
+//   * TMEM: accumulators in columns [0, 256) (N=128: main + cross, single buffer; N=64/32: two
+//     buffers), A ring of 4 stages x (32 hi + 32 lo) columns in [256, 512);
+//   * B ring in shared memory (TMA, 128B swizzle) with its own, deeper set of stages.
+// Warps: 0-7 A producers, 8 B producer (TMA), 9 MMA issuer + TMEM owner, 10-13 epilogue.
+template <int BN> struct Tc3Cfg {
+    static constexpr int B_BYTES = BN * 128;
+    static constexpr int BSTAGES = (192 * 1024) / (2 * B_BYTES) > 8 ? 8 : (192 * 1024) / (2 * B_BYTES);
+    static constexpr int ASTAGES = 4;
+    static constexpr int SMEM_BYTES = BSTAGES * 2 * B_BYTES + 1024 + 512;
+    static constexpr int NMAIN = BN == 32 ? 3 : 1;
+    static constexpr int NBUF = BN == 128 ? 1 : 2;
+    static constexpr int BUF_COLS = (NMAIN + 1) * BN;                     // 256 / 128 / 128
+    static constexpr int A_COL0 = 256;                                    // A ring: columns [256, 512)
+    static constexpr int TMEM_COLS = 512;
+    static_assert(NBUF * BUF_COLS <= A_COL0, "accumulators overlap the A ring");
+};
+
+__device__ __forceinline__ bool elect_one_sync() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.b32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
+// D[tmem] (+)= A[tmem] * B[smem descriptor]
+__device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};"
+        ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
+          "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]) : "memory");
+}
+
+// RAWB (G6D_CONV_TC_V=4): the weight tiles are the dominant L2 -> SM stream of this kernel (hi + lo =
+// 2 x BN x 128 B per K-block, against 16 KB of gathered A); with RAWB only the UNSPLIT fp32 tile is
+// loaded (map_hi = raw weights, map_lo unused).  The tensor core reads it as the hi operand (it
+// ignores the 13 low mantissa bits, i.e. hi = trunc(w)) and the producer warps derive
+// lo = rn_tf32(w - trunc(w)) from it in shared memory, halving the weight traffic.
+template <int BN, bool RAWB>
+__global__ void __launch_bounds__(TC2_THREADS, 1)
+conv_tc3_kernel(const ConvTcP p, const Tc2Work wk, const __grid_constant__ CUtensorMap map_hi,
+                const __grid_constant__ CUtensorMap map_lo) {
+    using Cfg = Tc3Cfg<BN>;
+    constexpr int BS = Cfg::BSTAGES, AS = Cfg::ASTAGES, NMAIN = Cfg::NMAIN, NBUF = Cfg::NBUF;
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t* base_ptr = smem_raw + (base - smem_u32(smem_raw));
+    const uint32_t bar_base = base + BS * 2 * Cfg::B_BYTES;
+    auto b_hi = [&](int s) { return base + s * 2 * Cfg::B_BYTES; };
+    auto b_lo = [&](int s) { return base + s * 2 * Cfg::B_BYTES + Cfg::B_BYTES; };
+    auto full_a = [&](int s) { return bar_base + 8 * s; };
+    auto empty_a = [&](int s) { return bar_base + 8 * (AS + s); };
+    auto full_b = [&](int s) { return bar_base + 8 * (2 * AS + s); };
+    auto empty_b = [&](int s) { return bar_base + 8 * (2 * AS + BS + s); };
+    auto tmem_full = [&](int b) { return bar_base + 8 * (2 * AS + 2 * BS + b); };
+    auto tmem_empty = [&](int b) { return bar_base + 8 * (2 * AS + 2 * BS + 2 + b); };
+    auto raw_full = [&](int s) { return bar_base + 8 * (2 * AS + 2 * BS + 4 + s); };
+    volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(base_ptr + BS * 2 * Cfg::B_BYTES + 8 * (2 * AS + 3 * BS + 4));
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (warp == 8 && lane == 0) {
+        for (int s = 0; s < AS; ++s) { mbar_init(full_a(s), 8); mbar_init(empty_a(s), 1); }
+        for (int s = 0; s < BS; ++s) { mbar_init(full_b(s), RAWB ? 8 : 1); mbar_init(empty_b(s), 1); mbar_init(raw_full(s), 1); }
+        for (int b = 0; b < 2; ++b) { mbar_init(tmem_full(b), 1); mbar_init(tmem_empty(b), 4); }
+        fence_barrier_init();
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_hi) : "memory");
+        if (!RAWB) asm volatile("prefetch.tensormap [%0];" ::"l"(&map_lo) : "memory");
+    }
+    if (warp == 9) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+                     ::"r"(smem_u32((const void*)tmem_slot)), "n"(Cfg::TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem0 = *tmem_slot;
+
+    auto decode = [&](int w, int& mt, int& nt, int& sp) {
+        nt = w % wk.n_tiles; w /= wk.n_tiles;
+        mt = w % wk.m_tiles;
+        sp = w / wk.m_tiles;
+    };
+
+    if (warp < 8) {
+        // =============================== A producers ===============================
+        const int quad = warp & 3, half = warp >> 2;
+        const int row = quad * 32 + lane;
+        const int cofs = half * 16;                                   // this thread's 16 channels of the K-block
+        const uint32_t lane_addr = tmem0 + ((uint32_t)(quad * 32) << 16) + (uint32_t)(Cfg::A_COL0 + cofs);
+        int git = 0;
+        for (int w = blockIdx.x; w < wk.total; w += gridDim.x) {
+            int mt, nt, sp;
+            decode(w, mt, nt, sp);
+            const int kb_begin = sp * p.kb_per_split;
+            const int nkb = min(p.kblocks, kb_begin + p.kb_per_split) - kb_begin;
+            int m = mt * TC_BM + row;
+            const bool rvalid = m < p.M;
+            if (!rvalid) m = 0;
+            const int xo = m % p.Wo; m /= p.Wo;
+            const int yo = m % p.Ho; m /= p.Ho;
+            const int zo = m % p.Do; m /= p.Do;
+            const int rb = m;
+            const int z0 = zo * p.stride - p.pd, y0 = yo * p.stride - p.ph, x0 = xo * p.stride - p.pw;
+            const int rsp = (z0 * p.H + y0) * p.W + x0;              // spatial index of tap (0,0,0); may be negative
+            const long long rbase = (long long)rb * p.D * p.H * p.W + rsp;
+            const long long grp = rb / (int)p.group_rows;
+            int c0, kx, ky, kz;
+            {
+                const int k = kb_begin * TC_BK;
+                int tap = 0; c0 = k;
+                if (p.K != p.Cin) { tap = k / p.Cin; c0 = k - tap * p.Cin; }
+                kx = tap % p.kw; const int tq = tap / p.kw; ky = tq % p.kh; kz = tq / p.kh;
+            }
+            float4 v[3][4];
+            bool ok[3]; int kc[3]; int ksp[3];
+            auto issue_loads = [&](int q) {
+                const int tap_sp = (kz * p.H + ky) * p.W + kx;
+                kc[q] = c0 + cofs; ksp[q] = tap_sp;
+                ok[q] = rvalid && (unsigned)(z0 + kz) < (unsigned)p.D && (unsigned)(y0 + ky) < (unsigned)p.H &&
+                        (unsigned)(x0 + kx) < (unsigned)p.W;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) v[q][j] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (ok[q]) {
+                    const float4* src = reinterpret_cast<const float4*>(p.x + p.ico + (rbase + tap_sp) * p.ics + c0 + cofs);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) v[q][j] = __ldg(src + j);
+                }
+                c0 += TC_BK;
+                if (c0 == p.Cin) { c0 = 0; if (++kx == p.kw) { kx = 0; if (++ky == p.kh) { ky = 0; ++kz; } } }
+            };
+            auto process = [&](int q, int it) {
+                const int g_it = git + it;
+                const int s = g_it % AS;
+                const uint32_t n_use = g_it / AS;
+                if (p.pro != G6D_PRO_NONE && ok[q]) {
+                    const float4* scp; const float4* shp;
+                    if (p.pro == G6D_PRO_CORR) {
+                        scp = reinterpret_cast<const float4*>(p.ps + (long long)(rsp + ksp[q]) * p.Cin + kc[q]);
+                        shp = reinterpret_cast<const float4*>(p.pb + kc[q]);
+                    } else {
+                        scp = reinterpret_cast<const float4*>(p.ps + grp * p.Cin + kc[q]);
+                        shp = reinterpret_cast<const float4*>(p.pb + grp * p.Cin + kc[q]);
+                    }
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const float4 sc = __ldg(scp + j), sh = __ldg(shp + j);
+                        float4 x4 = v[q][j];
+                        x4.x = fmaf(x4.x, sc.x, sh.x); x4.y = fmaf(x4.y, sc.y, sh.y);
+                        x4.z = fmaf(x4.z, sc.z, sh.z); x4.w = fmaf(x4.w, sc.w, sh.w);
+                        if (p.pro == G6D_PRO_AFFINE_RELU) {
+                            x4.x = fmaxf(x4.x, 0.f); x4.y = fmaxf(x4.y, 0.f); x4.z = fmaxf(x4.z, 0.f); x4.w = fmaxf(x4.w, 0.f);
+                        }
+                        v[q][j] = x4;
+                    }
+                }
+                uint32_t hi[16], lo[16];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const float xs[4] = {v[q][j].x, v[q][j].y, v[q][j].z, v[q][j].w};
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const uint32_t h = (__float_as_uint(xs[e]) + 0x1000u) & 0xFFFFE000u;
+                        hi[j * 4 + e] = h;
+                        lo[j * 4 + e] = __float_as_uint(xs[e] - __uint_as_float(h));
+                    }
+                }
+                mbar_wait(empty_a(s), (n_use & 1) ^ 1, 1, g_it);
+                tc_fence_after();
+                const uint32_t ta = lane_addr + (uint32_t)(s * 64);
+                tmem_st16(ta, hi);
+                tmem_st16(ta + 32, lo);
+                asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(full_a(s));
+                if (RAWB) {
+                    // weight tile of the same K-block: lo = rn_tf32(w - trunc(w)), elementwise on the swizzled tile
+                    const int sb = g_it % BS;
+                    mbar_wait(raw_full(sb), (g_it / BS) & 1, 7, g_it);
+#pragma unroll
+                    for (int ch = 0; ch < BN * 8 / 256; ++ch) {
+                        const uint32_t off = (uint32_t)((ch * 256 + (int)threadIdx.x) * 16);
+                        float4 wv;
+                        asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(wv.x), "=f"(wv.y), "=f"(wv.z), "=f"(wv.w) : "r"(b_hi(sb) + off) : "memory");
+                        auto lo_of = [](float w) {
+                            const float d = w - __uint_as_float(__float_as_uint(w) & 0xFFFFE000u);
+                            return __uint_as_float((__float_as_uint(d) + 0x1000u) & 0xFFFFE000u);
+                        };
+                        asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(b_lo(sb) + off), "f"(lo_of(wv.x)), "f"(lo_of(wv.y)), "f"(lo_of(wv.z)), "f"(lo_of(wv.w)) : "memory");
+                    }
+                    fence_proxy_async();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(full_b(sb));
+                }
+            };
+            if (nkb > 0) issue_loads(0);
+            if (nkb > 1) issue_loads(1);
+            for (int it = 0; it < nkb; it += 3) {
+                if (it + 2 < nkb) issue_loads(2);
+                process(0, it);
+                if (it + 1 < nkb) {
+                    if (it + 3 < nkb) issue_loads(0);
+                    process(1, it + 1);
+                }
+                if (it + 2 < nkb) {
+                    if (it + 4 < nkb) issue_loads(1);
+                    process(2, it + 2);
+                }
+            }
+            git += nkb;
+        }
+    } else if (warp == 8) {
+        // =============================== B producer (TMA) ===============================
+        if (lane == 0) {
+            int git = 0;
+            for (int w = blockIdx.x; w < wk.total; w += gridDim.x) {
+                int mt, nt, sp;
+                decode(w, mt, nt, sp);
+                const int kb_begin = sp * p.kb_per_split;
+                const int nkb = min(p.kblocks, kb_begin + p.kb_per_split) - kb_begin;
+                for (int it = 0; it < min(nkb, TC2_PF); ++it) {
+                    tma_prefetch_2d(&map_hi, (kb_begin + it) * TC_BK, nt * BN);
+                    tma_prefetch_2d(&map_lo, (kb_begin + it) * TC_BK, nt * BN);
+                }
+                for (int it = 0; it < nkb; ++it, ++git) {
+                    const int s = git % BS;
+                    if (it + TC2_PF < nkb) {
+                        tma_prefetch_2d(&map_hi, (kb_begin + it + TC2_PF) * TC_BK, nt * BN);
+                        tma_prefetch_2d(&map_lo, (kb_begin + it + TC2_PF) * TC_BK, nt * BN);
+                    }
+                    mbar_wait(empty_b(s), ((git / BS) & 1) ^ 1, 3, git);
+                    const int k = (kb_begin + it) * TC_BK;
+                    if (RAWB) {
+                        mbar_expect_tx(raw_full(s), Cfg::B_BYTES);
+                        tma_load_2d(b_hi(s), &map_hi, raw_full(s), k, nt * BN);
+                    } else {
+                        mbar_expect_tx(full_b(s), 2 * Cfg::B_BYTES);
+                        tma_load_2d(b_hi(s), &map_hi, full_b(s), k, nt * BN);
+                        tma_load_2d(b_lo(s), &map_lo, full_b(s), k, nt * BN);
+                    }
+                }
+            }
+        }
+    } else if (warp == 9) {
+        // =============================== MMA issuer ===============================
+        if (elect_one_sync()) {
+            const uint32_t idesc = umma_idesc_tf32(TC_BM, BN);
+            int git = 0, tile = 0;
+            for (int w = blockIdx.x; w < wk.total; w += gridDim.x, ++tile) {
+                int mt, nt, sp;
+                decode(w, mt, nt, sp);
+                const int kb_begin = sp * p.kb_per_split;
+                const int nkb = min(p.kblocks, kb_begin + p.kb_per_split) - kb_begin;
+                const int buf = tile % NBUF;
+                mbar_wait(tmem_empty(buf), ((tile / NBUF) & 1) ^ 1, 6, tile);     // epilogue has drained this buffer
+                tc_fence_after();
+                const uint32_t acc0 = tmem0 + (uint32_t)(buf * Cfg::BUF_COLS);
+                const uint32_t cross_acc = acc0 + (uint32_t)(NMAIN * BN);
+                for (int it = 0; it < nkb; ++it, ++git) {
+                    const int sa = git % AS, sb = git % BS;
+                    mbar_wait(full_a(sa), (git / AS) & 1, 4, git);
+                    mbar_wait(full_b(sb), (git / BS) & 1, 5, git);
+                    tc_fence_after();
+                    const uint32_t ah = tmem0 + (uint32_t)(Cfg::A_COL0 + sa * 64), al = ah + 32;
+                    const uint64_t dbh = umma_desc_sw128(b_hi(sb)), dbl = umma_desc_sw128(b_lo(sb));
+                    const uint32_t main_acc = acc0 + (uint32_t)((it % NMAIN) * BN);
+#pragma unroll
+                    for (int ks = 0; ks < TC_BK / 8; ++ks) {
+                        const uint64_t adv = (uint64_t)((ks * 32) >> 4);
+                        umma_tf32_ts(cross_acc, al + ks * 8, dbh + adv, idesc, (it > 0 || ks > 0) ? 1u : 0u);
+                        umma_tf32_ts(cross_acc, ah + ks * 8, dbl + adv, idesc, 1u);
+                        umma_tf32_ts(main_acc, ah + ks * 8, dbh + adv, idesc, (it >= NMAIN || ks > 0) ? 1u : 0u);
+                    }
+                    umma_commit(empty_a(sa));
+                    umma_commit(empty_b(sb));
+                }
+                umma_commit(tmem_full(buf));
+            }
+        }
+    } else {
+        // =============================== epilogue (warps 10-13) ===============================
+        const int quad = warp & 3;                     // TMEM lane quadrant = warp id % 4
+        int tile = 0;
+        for (int w = blockIdx.x; w < wk.total; w += gridDim.x, ++tile) {
+            int mt, nt, sp;
+            decode(w, mt, nt, sp);
+            const int kb_begin = sp * p.kb_per_split;
+            const int nkb = min(p.kblocks, kb_begin + p.kb_per_split) - kb_begin;
+            const int buf = tile % NBUF;
+            mbar_wait(tmem_full(buf), (tile / NBUF) & 1, 2, tile);
+            tc_fence_after();
+            const int m = mt * TC_BM + quad * 32 + lane;
+            const int n_base = nt * BN;
+            const bool partial = p.splits > 1;
+            const bool vec_ok = partial ? (p.Cout & 3) == 0
+                                        : ((p.ocs & 3) == 0 && (p.oco & 3) == 0 && (reinterpret_cast<uintptr_t>(p.y) & 15) == 0 &&
+                                           (!p.bias || (reinterpret_cast<uintptr_t>(p.bias) & 15) == 0));
+            const int n_acc = nkb < NMAIN ? nkb : NMAIN;
+            const uint32_t tbase = tmem0 + (uint32_t)(buf * Cfg::BUF_COLS) + ((uint32_t)(quad * 32) << 16);
+#pragma unroll 1
+            for (int cc = 0; cc < BN; cc += 16) {
+                float accv[16];
+#pragma unroll
+                for (int a = 0; a <= NMAIN; ++a) {
+                    const bool used = a == NMAIN || a < n_acc;
+                    uint32_t r[16];
+                    if (used) {
+                        asm volatile(
+                            "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                            : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                              "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+                            : "r"(tbase + (uint32_t)(a * BN + cc)));
+                        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) accv[j] = a == 0 ? __uint_as_float(r[j]) : accv[j] + __uint_as_float(r[j]);
+                    }
+                }
+                if (m < p.M) {
+                    const int n0 = n_base + cc;
+                    float* dst = partial ? p.ws + ((long long)sp * p.M + m) * p.Cout + n0
+                                         : p.y + (long long)m * p.ocs + p.oco + n0;
+                    const bool vec = vec_ok && n0 + 16 <= p.Cout;
+                    if (vec) {
+#pragma unroll
+                        for (int j4 = 0; j4 < 4; ++j4) {
+                            float4 v = make_float4(accv[j4 * 4], accv[j4 * 4 + 1], accv[j4 * 4 + 2], accv[j4 * 4 + 3]);
+                            if (!partial) {
+                                if (p.bias) {
+                                    const float4 bb = __ldg(reinterpret_cast<const float4*>(p.bias + n0) + j4);
+                                    v.x += bb.x; v.y += bb.y; v.z += bb.z; v.w += bb.w;
+                                }
+                                v.x = tc_act(v.x, p.act); v.y = tc_act(v.y, p.act); v.z = tc_act(v.z, p.act); v.w = tc_act(v.w, p.act);
+                            }
+                            reinterpret_cast<float4*>(dst)[j4] = v;
+                        }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) {
+                            if (n0 + j < p.Cout) {
+                                float v = accv[j];
+                                if (!partial) {
+                                    if (p.bias) v += __ldg(p.bias + n0 + j);
+                                    v = tc_act(v, p.act);
+                                }
+                                dst[j] = v;
+                            }
+                        }
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tmem_empty(buf));
+        }
+    }
+    __syncthreads();
+    if (warp == 9) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem0), "n"(Cfg::TMEM_COLS) : "memory");
+    }
+}
+
 __global__ void conv_tc_reduce_kernel(const float* __restrict__ ws, const float* __restrict__ bias,
                                       float* __restrict__ y, int M, int Cout, int splits, int ocs, int oco, int act) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -800,8 +1178,27 @@ static int launch_tc(const ConvTcP& p, const CUtensorMap& mh, const CUtensorMap&
 
 static int tc_version() {
     static int v = -1;
-    if (v < 0) { const char* e = getenv("G6D_CONV_TC_V"); v = (e && e[0] == '1') ? 1 : 2; }
+    if (v < 0) { const char* e = getenv("G6D_CONV_TC_V"); v = (e && e[0] >= '1' && e[0] <= '4') ? e[0] - '0' : 2; }
     return v;
+}
+
+template <int BN, bool RAWB>
+static int launch_tc3(const ConvTcP& p, const CUtensorMap& mh, const CUtensorMap& ml, cudaStream_t st) {
+    using Cfg = Tc3Cfg<BN>;
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(conv_tc3_kernel<BN, RAWB>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+        if (e != cudaSuccess) { set_error("g6d_conv_tc: cannot opt in to %d B of shared memory: %s", Cfg::SMEM_BYTES, cudaGetErrorString(e)); return G6D_ECUDA; }
+        configured = true;
+    }
+    Tc2Work wk;
+    wk.m_tiles = ceil_div(p.M, TC_BM); wk.n_tiles = ceil_div(p.Cout, BN);
+    const long long total = (long long)wk.m_tiles * wk.n_tiles * p.splits;
+    wk.total = (int)total;
+    const int grid = total < kNumSMs ? (int)total : kNumSMs;
+    conv_tc3_kernel<BN, RAWB><<<grid, TC2_THREADS, Cfg::SMEM_BYTES, st>>>(p, wk, mh, ml);
+    G6D_CHECK_LAUNCH("g6d_conv_tc(v3)");
+    return G6D_OK;
 }
 
 template <int BN>
@@ -835,7 +1232,7 @@ __global__ void split_tf32_kernel(const float* __restrict__ in, float* __restric
 
 // [Cout, Cin, taps] (reference layout) -> hi/lo [rows_pad, taps*Cin_pad], K index = tap*Cin_pad + c
 __global__ void pack_conv_weight_tc_kernel(const float* __restrict__ w, float* __restrict__ hi, float* __restrict__ lo,
-                                           int Cout, int Cin, int Cin_pad, int taps, int rows_pad,
+                                           float* __restrict__ raw, int Cout, int Cin, int Cin_pad, int taps, int rows_pad,
                                            const float* __restrict__ scale) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const long long K = (long long)taps * Cin_pad;
@@ -851,6 +1248,7 @@ __global__ void pack_conv_weight_tc_kernel(const float* __restrict__ w, float* _
     const float h = to_tf32(v);
     hi[i] = h;
     lo[i] = to_tf32(v - h);
+    if (raw) raw[i] = v;
 }
 
 // ==========================================================================================
@@ -1248,7 +1646,7 @@ extern "C" long long g6d_conv_tc_workspace_bytes(const g6d_conv_desc* desc) {
 }
 
 extern "C" int g6d_conv_tc(const g6d_conv_desc* desc, const float* x, const float* w_hi, const float* w_lo,
-                           int w_rows, const float* bias, const float* pro_scale, const float* pro_shift, float* y,
+                           const float* w_raw, int w_rows, const float* bias, const float* pro_scale, const float* pro_shift, float* y,
                            void* ws, g6d_stream_t stream) {
     {   // stride-1 multi-tap convolutions: A-reuse kernel
         ConvFlatP fp{}; int smem = 0;
@@ -1294,7 +1692,17 @@ extern "C" int g6d_conv_tc(const g6d_conv_desc* desc, const float* x, const floa
     const bool v2_ok = p.D + p.pd + 8 < 256 && p.H + p.ph + 8 < 4096 && p.W + p.pw + 8 < 4096 &&
                        (long long)p.D * p.H * p.W < (1ll << 30) && p.group_rows < (1ll << 31);
     if (bn == 256) rc = launch_tc<256>(p, mh, ml, st);
-    else if (tc_version() == 2 && v2_ok) {
+    else if (tc_version() == 4 && v2_ok && w_raw) { // A operand in tensor memory, weights split in shared memory
+        CUtensorMap mr;
+        if ((rc = make_weight_map(&mr, w_raw, w_rows, p.K, bn)) != G6D_OK) return rc;
+        if (bn == 128) rc = launch_tc3<128, true>(p, mr, mr, st);
+        else if (bn == 64) rc = launch_tc3<64, true>(p, mr, mr, st);
+        else rc = launch_tc3<32, true>(p, mr, mr, st);
+    } else if (tc_version() >= 3 && v2_ok) {        // A operand in tensor memory
+        if (bn == 128) rc = launch_tc3<128, false>(p, mh, ml, st);
+        else if (bn == 64) rc = launch_tc3<64, false>(p, mh, ml, st);
+        else rc = launch_tc3<32, false>(p, mh, ml, st);
+    } else if (tc_version() == 2 && v2_ok) {
         if (bn == 128) rc = launch_tc2<128>(p, mh, ml, st);
         else if (bn == 64) rc = launch_tc2<64>(p, mh, ml, st);
         else rc = launch_tc2<32>(p, mh, ml, st);
@@ -1319,13 +1727,13 @@ extern "C" int g6d_split_tf32(const float* in, float* hi, float* lo, long long n
     return G6D_OK;
 }
 
-extern "C" int g6d_pack_conv_weight_tc(const float* w, float* out_hi, float* out_lo, int Cout, int Cin, int Cin_pad,
+extern "C" int g6d_pack_conv_weight_tc(const float* w, float* out_hi, float* out_lo, float* out_raw, int Cout, int Cin, int Cin_pad,
                                        int taps, int rows_pad, const float* cout_scale, g6d_stream_t stream) {
     G6D_REQUIRE(w && out_hi && out_lo && Cout > 0 && Cin > 0 && Cin_pad >= Cin && taps > 0 && rows_pad >= Cout,
                 "g6d_pack_conv_weight_tc: bad args");
     const long long total = (long long)taps * Cin_pad * rows_pad;
-    pack_conv_weight_tc_kernel<<<ceil_div(total, 256), 256, 0, as_stream(stream)>>>(w, out_hi, out_lo, Cout, Cin, Cin_pad,
-                                                                                    taps, rows_pad, cout_scale);
+    pack_conv_weight_tc_kernel<<<ceil_div(total, 256), 256, 0, as_stream(stream)>>>(w, out_hi, out_lo, out_raw, Cout, Cin,
+                                                                                    Cin_pad, taps, rows_pad, cout_scale);
     G6D_CHECK_LAUNCH("g6d_pack_conv_weight_tc");
     return G6D_OK;
 }

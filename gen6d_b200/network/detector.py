@@ -60,6 +60,7 @@ class Detector(PackedModule):
             pc = ops.PackedConv(ops.transpose_to_packed(flat), None, c, rfn, (1, k, k), 1, (0, k // 2, k // 2))
             if rfn >= 16:   # channels-last features [rfn, (ky,kx,c)] are already the K-major B operand
                 pc.w_hi, pc.w_lo = ops.split_tf32(flat)
+                pc.w_raw = flat
             kernels.append(pc)
         self.ref_kernels = kernels
         self.stages.clear()             # captured graphs hold pointers to the previous reference set

@@ -223,6 +223,7 @@ class PackedConv:
     pad: tuple = (0, 0, 0)
     w_hi: Optional[torch.Tensor] = None   # tensor-core path: [rows, K] tf32 hi / lo split (K-major)
     w_lo: Optional[torch.Tensor] = None
+    w_raw: Optional[torch.Tensor] = None  # the same matrix unsplit (G6D_CONV_TC_V=4 kernel splits it in shared memory)
 
 
 def conv_path():
@@ -255,7 +256,8 @@ def pack_conv(weight, bias=None, stride=1, pad=None, cin_pad=None, cout_scale=No
         rows = (cout + 7) // 8 * 8
         pc.w_hi = torch.empty(rows, taps * cin_pad, device=w.device, dtype=torch.float32)
         pc.w_lo = torch.empty_like(pc.w_hi)
-        _call('g6d_pack_conv_weight_tc', _p(w), _p(pc.w_hi), _p(pc.w_lo), cout, cin, cin_pad, taps, rows,
+        pc.w_raw = torch.empty_like(pc.w_hi)
+        _call('g6d_pack_conv_weight_tc', _p(w), _p(pc.w_hi), _p(pc.w_lo), _p(pc.w_raw), cout, cin, cin_pad, taps, rows,
               _p(cout_scale.contiguous()) if cout_scale is not None else None, _stream())
     return pc
 
@@ -299,7 +301,7 @@ def conv(x, pc, prologue=PRO_NONE, pro_scale=None, pro_shift=None, group_rows=1,
         if nbytes < 0:
             _lib.check(-1, 'g6d_conv_tc_workspace_bytes')
         ws = torch.empty(nbytes // 4, device=x.device, dtype=torch.float32) if nbytes > 0 else None
-        _call('g6d_conv_tc', C.byref(d), _p(x), _p(pc.w_hi), _p(pc.w_lo), pc.w_hi.shape[0], _p(pc.bias), _p(pro_scale),
+        _call('g6d_conv_tc', C.byref(d), _p(x), _p(pc.w_hi), _p(pc.w_lo), _p(pc.w_raw), pc.w_hi.shape[0], _p(pc.bias), _p(pro_scale),
               _p(pro_shift), _p(out), _p(ws), _stream(), work=work,
               tag=f'M={B * Do * Ho * Wo} N={pc.cout} K={kd * kh * kw * pc.cin} k={kd}x{kh}x{kw} s={s} pro={prologue}')
         return out

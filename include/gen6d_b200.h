@@ -153,19 +153,22 @@ int g6d_pack_conv_weight(const float* w, float* out, int Cout, int Cin, int Cin_
  * Same contract as g6d_conv, for problems with Cin % 32 == 0 and Cout >= 16
  * (g6d_conv_tc_supported).  Weights are pre-split [w_rows >= Cout, K] K-major arrays
  * (K = tap*Cin + c): w_hi = tf32(w), w_lo = tf32(w - w_hi), see g6d_pack_conv_weight_tc /
- * g6d_split_tf32.  A tiles are gathered + transformed by producer warps, B tiles arrive by TMA,
- * accumulators live in TMEM. */
+ * g6d_split_tf32.  w_raw (optional, may be NULL) is the same matrix unsplit: the G6D_CONV_TC_V=4
+ * kernel streams only it and derives the lo half in shared memory (half the weight traffic).
+ * A tiles are gathered + transformed by producer warps, B tiles arrive by TMA, accumulators live
+ * in TMEM. */
 int g6d_conv_tc_supported(const g6d_conv_desc* desc);
 /* debug probe: D[128x32] = A[shift..shift+128) x I for a row-shifted SWIZZLE_128B descriptor (mode: base_offset rule) */
 int g6d_debug_umma_shift(float* out, int shift, int mode, g6d_stream_t stream);
 /* debug: host_out8[0] != 0 if a pipeline wait inside g6d_conv_tc timed out (kernel bailed out); syncs */
 int g6d_conv_tc_debug(int* host_out8);
 long long g6d_conv_tc_workspace_bytes(const g6d_conv_desc* desc);
-int g6d_conv_tc(const g6d_conv_desc* desc, const float* x, const float* w_hi, const float* w_lo, int w_rows,
-                const float* bias, const float* pro_scale, const float* pro_shift, float* y, void* ws,
+int g6d_conv_tc(const g6d_conv_desc* desc, const float* x, const float* w_hi, const float* w_lo,
+                const float* w_raw, int w_rows, const float* bias, const float* pro_scale, const float* pro_shift, float* y, void* ws,
                 g6d_stream_t stream);
-/* [Cout, Cin, taps] (reference layout) -> hi/lo [rows_pad, taps*Cin_pad]; optional BN-fold scale */
-int g6d_pack_conv_weight_tc(const float* w, float* out_hi, float* out_lo, int Cout, int Cin, int Cin_pad, int taps,
+/* [Cout, Cin, taps] (reference layout) -> hi/lo (and, if out_raw != NULL, unsplit) [rows_pad, taps*Cin_pad];
+ * optional BN-fold scale */
+int g6d_pack_conv_weight_tc(const float* w, float* out_hi, float* out_lo, float* out_raw, int Cout, int Cin, int Cin_pad, int taps,
                             int rows_pad, const float* cout_scale, g6d_stream_t stream);
 /* hi = tf32(x), lo = tf32(x - hi), elementwise (detector reference features as kernels) */
 int g6d_split_tf32(const float* in, float* hi, float* lo, long long n, g6d_stream_t stream);
