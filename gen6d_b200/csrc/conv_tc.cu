@@ -736,7 +736,7 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16
 // loaded (map_hi = raw weights, map_lo unused).  The tensor core reads it as the hi operand (it
 // ignores the 13 low mantissa bits, i.e. hi = trunc(w)) and the producer warps derive
 // lo = rn_tf32(w - trunc(w)) from it in shared memory, halving the weight traffic.
-template <int BN, bool RAWB>
+template <int BN, bool RAWB, int PF = 2>
 __global__ void __launch_bounds__(TC2_THREADS, 1)
 conv_tc3_kernel(const ConvTcP p, const Tc2Work wk, const __grid_constant__ CUtensorMap map_hi,
                 const __grid_constant__ CUtensorMap map_lo) {
@@ -812,8 +812,10 @@ conv_tc3_kernel(const ConvTcP p, const Tc2Work wk, const __grid_constant__ CUten
                 if (p.K != p.Cin) { tap = k / p.Cin; c0 = k - tap * p.Cin; }
                 kx = tap % p.kw; const int tq = tap / p.kw; ky = tq % p.kh; kz = tq / p.kh;
             }
-            float4 v[3][4];
-            bool ok[3]; int kc[3]; int ksp[3];
+            // ring of R = PF + 1 register slots: PF K-blocks of loads in flight while one is processed
+            constexpr int R = PF + 1;
+            float4 v[R][4];
+            bool ok[R]; int kc[R]; int ksp[R];
             auto issue_loads = [&](int q) {
                 const int tap_sp = (kz * p.H + ky) * p.W + kx;
                 kc[q] = c0 + cofs; ksp[q] = tap_sp;
@@ -894,18 +896,16 @@ conv_tc3_kernel(const ConvTcP p, const Tc2Work wk, const __grid_constant__ CUten
                     if (lane == 0) mbar_arrive(full_b(sb));
                 }
             };
-            if (nkb > 0) issue_loads(0);
-            if (nkb > 1) issue_loads(1);
-            for (int it = 0; it < nkb; it += 3) {
-                if (it + 2 < nkb) issue_loads(2);
-                process(0, it);
-                if (it + 1 < nkb) {
-                    if (it + 3 < nkb) issue_loads(0);
-                    process(1, it + 1);
-                }
-                if (it + 2 < nkb) {
-                    if (it + 4 < nkb) issue_loads(1);
-                    process(2, it + 2);
+#pragma unroll
+            for (int q = 0; q < PF; ++q)
+                if (q < nkb) issue_loads(q);
+            for (int it = 0; it < nkb; it += R) {
+#pragma unroll
+                for (int q = 0; q < R; ++q) {
+                    if (it + q < nkb) {
+                        if (it + q + PF < nkb) issue_loads((q + PF) % R);
+                        process(q, it + q);
+                    }
                 }
             }
             git += nkb;
@@ -1182,12 +1182,19 @@ static int tc_version() {
     return v;
 }
 
-template <int BN, bool RAWB>
+static int tc3_prefetch() {      // K-blocks of activation loads in flight per producer thread (G6D_CONV_PF = 2 | 3)
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("G6D_CONV_PF"); v = (e && e[0] == '3') ? 3 : 2; }
+    return v;
+}
+
+template <int BN, bool RAWB, int PF = 2>
 static int launch_tc3(const ConvTcP& p, const CUtensorMap& mh, const CUtensorMap& ml, cudaStream_t st) {
     using Cfg = Tc3Cfg<BN>;
+    if (!RAWB && PF == 2 && tc3_prefetch() == 3) return launch_tc3<BN, false, 3>(p, mh, ml, st);
     static bool configured = false;
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(conv_tc3_kernel<BN, RAWB>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+        cudaError_t e = cudaFuncSetAttribute(conv_tc3_kernel<BN, RAWB, PF>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
         if (e != cudaSuccess) { set_error("g6d_conv_tc: cannot opt in to %d B of shared memory: %s", Cfg::SMEM_BYTES, cudaGetErrorString(e)); return G6D_ECUDA; }
         configured = true;
     }
@@ -1196,7 +1203,7 @@ static int launch_tc3(const ConvTcP& p, const CUtensorMap& mh, const CUtensorMap
     const long long total = (long long)wk.m_tiles * wk.n_tiles * p.splits;
     wk.total = (int)total;
     const int grid = total < kNumSMs ? (int)total : kNumSMs;
-    conv_tc3_kernel<BN, RAWB><<<grid, TC2_THREADS, Cfg::SMEM_BYTES, st>>>(p, wk, mh, ml);
+    conv_tc3_kernel<BN, RAWB, PF><<<grid, TC2_THREADS, Cfg::SMEM_BYTES, st>>>(p, wk, mh, ml);
     G6D_CHECK_LAUNCH("g6d_conv_tc(v3)");
     return G6D_OK;
 }
