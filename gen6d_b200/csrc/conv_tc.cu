@@ -699,17 +699,21 @@ conv_tc2_kernel(const ConvTcP p, const Tc2Work wk, const __grid_constant__ CUten
 //     buffers), A ring of 4 stages x (32 hi + 32 lo) columns in [256, 512);
 //   * B ring in shared memory (TMA, 128B swizzle) with its own, deeper set of stages.
 // Warps: 0-7 A producers, 8 B producer (TMA), 9 MMA issuer + TMEM owner, 10-13 epilogue.
-template <int BN> struct Tc3Cfg {
+template <int BN, bool STAGED = false> struct Tc3Cfg {
     static constexpr int B_BYTES = BN * 128;
-    static constexpr int BSTAGES = (192 * 1024) / (2 * B_BYTES) > 8 ? 8 : (192 * 1024) / (2 * B_BYTES);
+    static constexpr int RAW_BYTES = TC_BM * 128;                         // one unsplit A tile (STAGED)
+    static constexpr int BSTAGES = STAGED ? (BN == 128 ? 4 : (BN == 64 ? 6 : 8))
+                                          : ((192 * 1024) / (2 * B_BYTES) > 8 ? 8 : (192 * 1024) / (2 * B_BYTES));
+    static constexpr int RSTAGES = STAGED ? (BN == 128 ? 5 : (BN == 64 ? 6 : 8)) : 0;
     static constexpr int ASTAGES = 4;
-    static constexpr int SMEM_BYTES = BSTAGES * 2 * B_BYTES + 1024 + 512;
+    static constexpr int SMEM_BYTES = BSTAGES * 2 * B_BYTES + RSTAGES * RAW_BYTES + 1024 + 512;
     static constexpr int NMAIN = BN == 32 ? 3 : 1;
     static constexpr int NBUF = BN == 128 ? 1 : 2;
     static constexpr int BUF_COLS = (NMAIN + 1) * BN;                     // 256 / 128 / 128
     static constexpr int A_COL0 = 256;                                    // A ring: columns [256, 512)
     static constexpr int TMEM_COLS = 512;
     static_assert(NBUF * BUF_COLS <= A_COL0, "accumulators overlap the A ring");
+    static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
 };
 
 __device__ __forceinline__ bool elect_one_sync() {
@@ -736,16 +740,27 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16
 // loaded (map_hi = raw weights, map_lo unused).  The tensor core reads it as the hi operand (it
 // ignores the 13 low mantissa bits, i.e. hi = trunc(w)) and the producer warps derive
 // lo = rn_tf32(w - trunc(w)) from it in shared memory, halving the weight traffic.
-template <int BN, bool RAWB, int PF = 2>
+//
+// STAGED (G6D_CONV_TC_V=5): ncu showed that v3's thread-per-row gather (32 distinct 128-byte lines per
+// LDG.128) costs 8x the L1 data-pipe wavefronts of a coalesced one and saturates that pipe (93 % of
+// active cycles), just as the tensor core's operand reads + the producers' st.shared do in v2 (LSU 51 % +
+// TC 50 %).  STAGED keeps the coalesced access of v2 but never holds the tile in registers: the
+// producers issue cp.async (16 B, zero-fill for padding / rows >= M) into a ring of unsplit A tiles in
+// shared memory, RSTAGES - 1 K-blocks ahead (cp.async.mbarrier.arrive tracks completion), and later
+// read their own row back with bank-conflict-free swizzled ld.shared (4 wavefronts per LDS.128), split
+// it and tcgen05.st it to TMEM.  Data-pipe budget per K-block at N = 128: A 128 (cp.async fill) + 128
+// (LDS) wavefronts, B 256 (TMA fill) + 384 (MMA operand reads) = ~900, against ~1150-1280 in v2.
+template <int BN, bool RAWB, int PF = 2, bool STAGED = false>
 __global__ void __launch_bounds__(TC2_THREADS, 1)
 conv_tc3_kernel(const ConvTcP p, const Tc2Work wk, const __grid_constant__ CUtensorMap map_hi,
                 const __grid_constant__ CUtensorMap map_lo) {
-    using Cfg = Tc3Cfg<BN>;
-    constexpr int BS = Cfg::BSTAGES, AS = Cfg::ASTAGES, NMAIN = Cfg::NMAIN, NBUF = Cfg::NBUF;
+    using Cfg = Tc3Cfg<BN, STAGED>;
+    constexpr int BS = Cfg::BSTAGES, AS = Cfg::ASTAGES, NMAIN = Cfg::NMAIN, NBUF = Cfg::NBUF, RS = Cfg::RSTAGES;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t* base_ptr = smem_raw + (base - smem_u32(smem_raw));
-    const uint32_t bar_base = base + BS * 2 * Cfg::B_BYTES;
+    const uint32_t raw_base = base + BS * 2 * Cfg::B_BYTES;              // STAGED: ring of unsplit A tiles
+    const uint32_t bar_base = raw_base + RS * Cfg::RAW_BYTES;
     auto b_hi = [&](int s) { return base + s * 2 * Cfg::B_BYTES; };
     auto b_lo = [&](int s) { return base + s * 2 * Cfg::B_BYTES + Cfg::B_BYTES; };
     auto full_a = [&](int s) { return bar_base + 8 * s; };
@@ -755,13 +770,17 @@ conv_tc3_kernel(const ConvTcP p, const Tc2Work wk, const __grid_constant__ CUten
     auto tmem_full = [&](int b) { return bar_base + 8 * (2 * AS + 2 * BS + b); };
     auto tmem_empty = [&](int b) { return bar_base + 8 * (2 * AS + 2 * BS + 2 + b); };
     auto raw_full = [&](int s) { return bar_base + 8 * (2 * AS + 2 * BS + 4 + s); };
-    volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(base_ptr + BS * 2 * Cfg::B_BYTES + 8 * (2 * AS + 3 * BS + 4));
+    auto araw_full = [&](int s) { return bar_base + 8 * (2 * AS + 3 * BS + 4 + s); };
+    auto araw_empty = [&](int s) { return bar_base + 8 * (2 * AS + 3 * BS + 4 + RS + s); };
+    auto araw = [&](int s) { return raw_base + s * Cfg::RAW_BYTES; };
+    volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(base_ptr + (bar_base - base) + 8 * (2 * AS + 3 * BS + 4 + 2 * RS));
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (warp == 8 && lane == 0) {
         for (int s = 0; s < AS; ++s) { mbar_init(full_a(s), 8); mbar_init(empty_a(s), 1); }
         for (int s = 0; s < BS; ++s) { mbar_init(full_b(s), RAWB ? 8 : 1); mbar_init(empty_b(s), 1); mbar_init(raw_full(s), 1); }
         for (int b = 0; b < 2; ++b) { mbar_init(tmem_full(b), 1); mbar_init(tmem_empty(b), 4); }
+        for (int s = 0; s < RS; ++s) { mbar_init(araw_full(s), 256); mbar_init(araw_empty(s), 8); }
         fence_barrier_init();
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_hi) : "memory");
         if (!RAWB) asm volatile("prefetch.tensormap [%0];" ::"l"(&map_lo) : "memory");
@@ -789,6 +808,140 @@ conv_tc3_kernel(const ConvTcP p, const Tc2Work wk, const __grid_constant__ CUten
         const int cofs = half * 16;                                   // this thread's 16 channels of the K-block
         const uint32_t lane_addr = tmem0 + ((uint32_t)(quad * 32) << 16) + (uint32_t)(Cfg::A_COL0 + cofs);
         int git = 0;
+        if constexpr (STAGED) {
+            // copy mapping (coalesced, as v2): 16-byte chunk `cchunk` of rows cr0 + 32*j; process mapping: own row
+            const int cchunk = threadIdx.x & 7, cr0 = threadIdx.x >> 3;
+            constexpr int DEPTH = RS - 1;                                 // K-blocks of cp.async in flight
+            for (int w = blockIdx.x; w < wk.total; w += gridDim.x) {
+                int mt, nt, sp;
+                decode(w, mt, nt, sp);
+                const int kb_begin = sp * p.kb_per_split;
+                const int nkb = min(p.kblocks, kb_begin + p.kb_per_split) - kb_begin;
+                const long long plane_sz = (long long)p.D * p.H * p.W;
+                // ---- the 4 rows this thread copies
+                int rb[4], rsp4[4], rc[4];
+                unsigned rvmask = 0;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    int m = mt * TC_BM + cr0 + 32 * j;
+                    const bool v = m < p.M;
+                    if (!v) m = 0;
+                    const int xo = m % p.Wo; m /= p.Wo;
+                    const int yo = m % p.Ho; m /= p.Ho;
+                    const int zo = m % p.Do; m /= p.Do;
+                    rb[j] = m;
+                    const int z = zo * p.stride - p.pd, y = yo * p.stride - p.ph, x = xo * p.stride - p.pw;
+                    rsp4[j] = (z * p.H + y) * p.W + x;
+                    rc[j] = ((z + 8) << 24) | ((y + 8) << 12) | (x + 8);
+                    if (v) rvmask |= 1u << j;
+                }
+                // ---- the row this thread transforms
+                int m = mt * TC_BM + row;
+                const bool rvalid = m < p.M;
+                if (!rvalid) m = 0;
+                const int xo = m % p.Wo; m /= p.Wo;
+                const int yo = m % p.Ho; m /= p.Ho;
+                const int zo = m % p.Do; m /= p.Do;
+                const int z0 = zo * p.stride - p.pd, y0 = yo * p.stride - p.ph, x0 = xo * p.stride - p.pw;
+                const int rsp = (z0 * p.H + y0) * p.W + x0;
+                const long long grp = m / (int)p.group_rows;
+                // two cursors over (tap, channel block): one for the copies (ahead), one for the transforms
+                int ic0, ikx, iky, ikz, pc0, pkx, pky, pkz;
+                {
+                    const int k = kb_begin * TC_BK;
+                    int tap = 0; ic0 = k;
+                    if (p.K != p.Cin) { tap = k / p.Cin; ic0 = k - tap * p.Cin; }
+                    ikx = tap % p.kw; const int tq = tap / p.kw; iky = tq % p.kh; ikz = tq / p.kh;
+                    pc0 = ic0; pkx = ikx; pky = iky; pkz = ikz;
+                }
+                auto issue = [&](int it) {
+                    const int g_it = git + it;
+                    const int s = g_it % RS;
+                    mbar_wait(araw_empty(s), ((g_it / RS) & 1) ^ 1, 8, g_it);       // all 8 warps have read the previous tile
+                    const int tap_sp = (ikz * p.H + iky) * p.W + ikx;
+                    const float* xb = p.x + p.ico + cchunk * 4 + ic0;
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const int z = ((rc[j] >> 24) & 0xff) - 8 + ikz, y = ((rc[j] >> 12) & 0xfff) - 8 + iky, x = (rc[j] & 0xfff) - 8 + ikx;
+                        const bool inb = ((rvmask >> j) & 1u) && (unsigned)z < (unsigned)p.D && (unsigned)y < (unsigned)p.H &&
+                                         (unsigned)x < (unsigned)p.W;
+                        const float* src = inb ? xb + ((long long)rb[j] * plane_sz + rsp4[j] + tap_sp) * p.ics : p.x;
+                        const int r = cr0 + 32 * j;
+                        const uint32_t dst = araw(s) + r * 128 + ((cchunk ^ (r & 7)) << 4);
+                        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(inb ? 16 : 0) : "memory");
+                    }
+                    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(araw_full(s)) : "memory");
+                    ic0 += TC_BK;
+                    if (ic0 == p.Cin) { ic0 = 0; if (++ikx == p.kw) { ikx = 0; if (++iky == p.kh) { iky = 0; ++ikz; } } }
+                };
+                auto process = [&](int it) {
+                    const int g_it = git + it;
+                    const int s = g_it % RS, sa = g_it % AS;
+                    const bool ok = rvalid && (unsigned)(z0 + pkz) < (unsigned)p.D && (unsigned)(y0 + pky) < (unsigned)p.H &&
+                                    (unsigned)(x0 + pkx) < (unsigned)p.W;
+                    const int tap_sp = (pkz * p.H + pky) * p.W + pkx;
+                    const int kc = pc0 + cofs;
+                    mbar_wait(araw_full(s), (g_it / RS) & 1, 9, g_it);
+                    float4 v[4];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const uint32_t src = araw(s) + row * 128 + (((half * 4 + j) ^ (row & 7)) << 4);
+                        asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v[j].x), "=f"(v[j].y), "=f"(v[j].z), "=f"(v[j].w) : "r"(src) : "memory");
+                    }
+                    if (p.pro != G6D_PRO_NONE && ok) {                  // padding / rows >= M stay zero (zero-filled copies)
+                        const float4* scp; const float4* shp;
+                        if (p.pro == G6D_PRO_CORR) {
+                            scp = reinterpret_cast<const float4*>(p.ps + (long long)(rsp + tap_sp) * p.Cin + kc);
+                            shp = reinterpret_cast<const float4*>(p.pb + kc);
+                        } else {
+                            scp = reinterpret_cast<const float4*>(p.ps + grp * p.Cin + kc);
+                            shp = reinterpret_cast<const float4*>(p.pb + grp * p.Cin + kc);
+                        }
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const float4 sc = __ldg(scp + j), sh = __ldg(shp + j);
+                            float4 x4 = v[j];
+                            x4.x = fmaf(x4.x, sc.x, sh.x); x4.y = fmaf(x4.y, sc.y, sh.y);
+                            x4.z = fmaf(x4.z, sc.z, sh.z); x4.w = fmaf(x4.w, sc.w, sh.w);
+                            if (p.pro == G6D_PRO_AFFINE_RELU) {
+                                x4.x = fmaxf(x4.x, 0.f); x4.y = fmaxf(x4.y, 0.f); x4.z = fmaxf(x4.z, 0.f); x4.w = fmaxf(x4.w, 0.f);
+                            }
+                            v[j] = x4;
+                        }
+                    }
+                    uint32_t hi[16], lo[16];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const float xs[4] = {v[j].x, v[j].y, v[j].z, v[j].w};
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            const uint32_t h = (__float_as_uint(xs[e]) + 0x1000u) & 0xFFFFE000u;
+                            hi[j * 4 + e] = h;
+                            lo[j * 4 + e] = __float_as_uint(xs[e] - __uint_as_float(h));
+                        }
+                    }
+                    __syncwarp();                                       // every lane's ld.shared has returned (values consumed above)
+                    if (lane == 0) mbar_arrive(araw_empty(s));
+                    mbar_wait(empty_a(sa), ((g_it / AS) & 1) ^ 1, 1, g_it);
+                    tc_fence_after();
+                    const uint32_t ta = lane_addr + (uint32_t)(sa * 64);
+                    tmem_st16(ta, hi);
+                    tmem_st16(ta + 32, lo);
+                    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(full_a(sa));
+                    pc0 += TC_BK;
+                    if (pc0 == p.Cin) { pc0 = 0; if (++pkx == p.kw) { pkx = 0; if (++pky == p.kh) { pky = 0; ++pkz; } } }
+                };
+                for (int it = 0; it < min(nkb, DEPTH); ++it) issue(it);
+                for (int it = 0; it < nkb; ++it) {
+                    if (it + DEPTH < nkb) issue(it + DEPTH);
+                    process(it);
+                }
+                git += nkb;
+            }
+        } else
         for (int w = blockIdx.x; w < wk.total; w += gridDim.x) {
             int mt, nt, sp;
             decode(w, mt, nt, sp);
@@ -1178,7 +1331,7 @@ static int launch_tc(const ConvTcP& p, const CUtensorMap& mh, const CUtensorMap&
 
 static int tc_version() {
     static int v = -1;
-    if (v < 0) { const char* e = getenv("G6D_CONV_TC_V"); v = (e && e[0] >= '1' && e[0] <= '4') ? e[0] - '0' : 2; }
+    if (v < 0) { const char* e = getenv("G6D_CONV_TC_V"); v = (e && e[0] >= '1' && e[0] <= '5') ? e[0] - '0' : 2; }
     return v;
 }
 
@@ -1188,13 +1341,13 @@ static int tc3_prefetch() {      // K-blocks of activation loads in flight per p
     return v;
 }
 
-template <int BN, bool RAWB, int PF = 2>
+template <int BN, bool RAWB, int PF = 2, bool STAGED = false>
 static int launch_tc3(const ConvTcP& p, const CUtensorMap& mh, const CUtensorMap& ml, cudaStream_t st) {
-    using Cfg = Tc3Cfg<BN>;
-    if (!RAWB && PF == 2 && tc3_prefetch() == 3) return launch_tc3<BN, false, 3>(p, mh, ml, st);
+    using Cfg = Tc3Cfg<BN, STAGED>;
+    if (!RAWB && !STAGED && PF == 2 && tc3_prefetch() == 3) return launch_tc3<BN, false, 3>(p, mh, ml, st);
     static bool configured = false;
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(conv_tc3_kernel<BN, RAWB, PF>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+        cudaError_t e = cudaFuncSetAttribute(conv_tc3_kernel<BN, RAWB, PF, STAGED>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
         if (e != cudaSuccess) { set_error("g6d_conv_tc: cannot opt in to %d B of shared memory: %s", Cfg::SMEM_BYTES, cudaGetErrorString(e)); return G6D_ECUDA; }
         configured = true;
     }
@@ -1203,7 +1356,7 @@ static int launch_tc3(const ConvTcP& p, const CUtensorMap& mh, const CUtensorMap
     const long long total = (long long)wk.m_tiles * wk.n_tiles * p.splits;
     wk.total = (int)total;
     const int grid = total < kNumSMs ? (int)total : kNumSMs;
-    conv_tc3_kernel<BN, RAWB, PF><<<grid, TC2_THREADS, Cfg::SMEM_BYTES, st>>>(p, wk, mh, ml);
+    conv_tc3_kernel<BN, RAWB, PF, STAGED><<<grid, TC2_THREADS, Cfg::SMEM_BYTES, st>>>(p, wk, mh, ml);
     G6D_CHECK_LAUNCH("g6d_conv_tc(v3)");
     return G6D_OK;
 }
@@ -1705,6 +1858,10 @@ extern "C" int g6d_conv_tc(const g6d_conv_desc* desc, const float* x, const floa
         if (bn == 128) rc = launch_tc3<128, true>(p, mr, mr, st);
         else if (bn == 64) rc = launch_tc3<64, true>(p, mr, mr, st);
         else rc = launch_tc3<32, true>(p, mr, mr, st);
+    } else if (tc_version() == 5 && v2_ok) {        // A staged by cp.async in shared memory, operand in tensor memory
+        if (bn == 128) rc = launch_tc3<128, false, 2, true>(p, mh, ml, st);
+        else if (bn == 64) rc = launch_tc3<64, false, 2, true>(p, mh, ml, st);
+        else rc = launch_tc3<32, false, 2, true>(p, mh, ml, st);
     } else if (tc_version() >= 3 && v2_ok) {        // A operand in tensor memory
         if (bn == 128) rc = launch_tc3<128, false>(p, mh, ml, st);
         else if (bn == 64) rc = launch_tc3<64, false>(p, mh, ml, st);
