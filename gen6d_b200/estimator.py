@@ -11,6 +11,7 @@ import torch
 import yaml
 
 from . import geometry as G
+from . import ops
 from .network import name2network
 
 
@@ -23,6 +24,7 @@ class Gen6DEstimator:
         'detector': None,
         'refiner': None,
         'refine_iter': 3,
+        'device_build': False,    # True: cut the 64 + 5x64 reference crops of build() with the device warp kernel (row f2)
         'host_warps': False,      # True: keep the between-stage crops on the host in OpenCV, as the reference does
         'host_threads': None,     # OpenCV / torch-CPU threads for the host geometry (None: min(8, usable CPUs))
     }
@@ -61,13 +63,22 @@ class Gen6DEstimator:
         ids_all = database.get_img_ids()
         ref_ids = G.select_views_fps(database, ids_all, self.cfg['ref_view_num'])
         res = self.cfg['ref_resolution']
-        ref_imgs, ref_Ks, ref_poses, ref_Hs = G.normalize_reference_views(database, ref_ids, res, 0.05)
-        rots = []
-        import cv2
-        for ang in (-np.pi / 2, -np.pi / 4, 0, np.pi / 4, np.pi / 2):
-            M = G.similarity_2d((res / 2, res / 2), 1.0, ang, (res / 2, res / 2)).astype(np.float32)
-            rots.append(np.stack([cv2.warpPerspective(database.get_image(i), M @ ref_Hs[k], (res, res),
-                                                      flags=cv2.INTER_LINEAR) for k, i in enumerate(ref_ids)], 0))
+        on_device = self.cfg['device_build']
+        ref_imgs, ref_Ks, ref_poses, ref_Hs = G.normalize_reference_views(database, ref_ids, res, 0.05, warp=not on_device)
+        rot_Hs = [[G.similarity_2d((res / 2, res / 2), 1.0, ang, (res / 2, res / 2)).astype(np.float32) @ ref_Hs[k]
+                   for k in range(len(ref_ids))] for ang in (-np.pi / 2, -np.pi / 4, 0, np.pi / 4, np.pi / 2)]
+        if on_device:
+            # same bytes as the OpenCV path (g6d_warp_perspective_u8 is bit-exact), one launch per set
+            srcs = [torch.from_numpy(np.ascontiguousarray(database.get_image(i))).to(self.detector.device) for i in ref_ids]
+            cut = lambda Hs: ops.warp_perspective_u8(
+                torch.from_numpy(G.pack_warp_jobs(srcs, [G.perspective_dst_to_src(H) for H in Hs])).to(srcs[0].device),
+                len(srcs), res, res).cpu().numpy()
+            ref_imgs = cut(list(ref_Hs))
+            rots = [cut(Hs) for Hs in rot_Hs]
+        else:
+            import cv2
+            rots = [np.stack([cv2.warpPerspective(database.get_image(i), Hs[k], (res, res), flags=cv2.INTER_LINEAR)
+                              for k, i in enumerate(ref_ids)], 0) for Hs in rot_Hs]
         ref_imgs_rots = np.stack(rots, 0)  # an,rfn,h,w,3
         self.detector.load_ref_imgs(ref_imgs[:self.cfg['det_ref_view_num']])
         self.selector.load_ref_imgs(ref_imgs_rots, ref_poses, center, vert)
