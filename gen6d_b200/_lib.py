@@ -73,8 +73,10 @@ _SIGNATURES = {
     'g6d_sel_parse': [P, P, I, I, P, P, P],
     'g6d_ref_volume_fill': [P, P, P, P, P, P, I, I, I, I, I, I, I, I, P, P, P],
     'g6d_ref_pose_heads': [P, P, P, P, I, I, P],
+    'g6d_pose_errors_workspace_bytes': [I, I],
+    'g6d_pose_errors': [P, I, P, P, P, I, I, P, P, P],
 }
-_RESTYPE = {'g6d_conv_workspace_bytes': L, 'g6d_conv_tc_workspace_bytes': L, 'g6d_launch_count': L, 'g6d_last_error': C.c_char_p}
+_RESTYPE = {'g6d_pose_errors_workspace_bytes': L, 'g6d_conv_workspace_bytes': L, 'g6d_conv_tc_workspace_bytes': L, 'g6d_launch_count': L, 'g6d_last_error': C.c_char_p}
 
 _lib = None
 

@@ -253,6 +253,17 @@ int g6d_ref_volume_fill(const float* ref_feats, const float* que_feats, const fl
  * w [7, K] rows = fcr(4), fct(2), fcs(1).  out [M, 7] = (qw,qx,qy,qz, tx,ty, log2 scale). */
 int g6d_ref_pose_heads(const float* x, const float* w, const float* b, float* out, int M, int K, g6d_stream_t stream);
 
+/* ------------------------------------------------------------------ evaluation (row f4) ---- */
+/* utils/pose_utils.py:149-158,192-196 (compute_pose_errors / the symmetric branch of
+ * compute_metrics_impl) with utils/base_utils.py:256-265 project_points and :390-394: for each of
+ * n_poses (predicted, ground-truth) pairs, out[p] = (mean reprojection error in pixels, mean 3-D
+ * point error = ADD, mean closest-point error = ADD-S or NaN when symmetric == 0) over the n_pts
+ * object points.  pts [n_pts,3], poses [n_poses,3,4], Ks [n_poses,3,3], out [n_poses,3], all f32 on
+ * the device; ws: g6d_pose_errors_workspace_bytes(n_pts, n_poses) bytes. */
+long long g6d_pose_errors_workspace_bytes(int n_pts, int n_poses);
+int g6d_pose_errors(const float* pts, int n_pts, const float* poses_pr, const float* poses_gt, const float* Ks,
+                    int n_poses, int symmetric, float* out, void* ws, g6d_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -105,3 +105,38 @@ DET_STATS_EST = _syn.DET_SCORE_STATS
 
 def estimator_case():
     return {'db': dict(_syn.DATABASE), 'net_cfg': {}, 'query_id': '11'}
+
+
+def metrics_case(n_pts=700, n_poses=14, seed=77):
+    """Seeded inputs of the evaluation metrics: object points on a bumpy ellipsoid,
+    ground-truth poses in front of the camera, predictions = ground truth perturbed by amounts that
+    straddle the ADD-0.1d and Prj-5 thresholds (plus one pose whose points cross the camera plane)."""
+    rng = np.random.RandomState(seed)
+    d = rng.randn(n_pts, 3)
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    pts = (d * np.array([0.5, 0.8, 1.0]) * (0.8 + 0.2 * rng.rand(n_pts, 1))).astype(np.float32)
+    diameter = float(np.max(np.linalg.norm(pts[:, None] - pts[None], axis=2)))
+
+    def rot(v):
+        ang = np.linalg.norm(v)
+        if ang < 1e-12:
+            return np.eye(3)
+        k = v / ang
+        Kx = np.array([[0, -k[2], k[1]], [k[2], 0, -k[0]], [-k[1], k[0], 0]])
+        return np.eye(3) + np.sin(ang) * Kx + (1 - np.cos(ang)) * Kx @ Kx
+
+    gts, prs, Ks = [], [], []
+    for i in range(n_poses):
+        R = rot(rng.randn(3) * 1.5)
+        t = np.array([rng.randn() * 0.3, rng.randn() * 0.3, 4.0 + rng.rand() * 3])
+        gt = np.concatenate([R, t[:, None]], 1).astype(np.float32)
+        mag = [0.0, 0.002, 0.01, 0.03, 0.06, 0.12, 0.3][i % 7]
+        Rp = rot(rng.randn(3) * mag) @ R
+        tp = t + rng.randn(3) * mag * np.array([1, 1, 3])
+        if i == n_poses - 1:
+            tp = np.array([0.05, -0.02, 0.3])          # object straddles the camera plane: exercises the depth clamp
+        prs.append(np.concatenate([Rp, tp[:, None]], 1).astype(np.float32))
+        gts.append(gt)
+        f = 500 + 200 * rng.rand()
+        Ks.append(np.array([[f, 0, 320], [0, f, 240], [0, 0, 1]], np.float32))
+    return {'pts': pts, 'diameter': diameter, 'gt': np.stack(gts), 'pr': np.stack(prs), 'Ks': np.stack(Ks)}

@@ -30,3 +30,22 @@ def test_device_build_equals_host_build():
     dev, _ = build_estimator(device_build=True)
     np.testing.assert_array_equal(dev.ref_info['imgs'], host.ref_info['imgs'])
     np.testing.assert_array_equal(dev.ref_info['ref_imgs'], host.ref_info['ref_imgs'])
+
+
+def test_pose_error_metrics_match_reference():
+    """g6d_pose_errors / gen6d_b200.metrics (row f4) against the goldens of the unmodified reference and the oracle."""
+    from golden import cases
+    from gen6d_b200 import metrics as M
+    from oracle import metrics as OM
+    c = cases.metrics_case()
+    Gm = np.load(os.path.join(ROOT, 'tests', 'golden', 'metrics_golden.npz'))
+    err = M.pose_errors(c['pts'], c['pr'], c['gt'], c['Ks'], symmetric=True).cpu().numpy()
+    np.testing.assert_allclose(err[:, 0], Gm['prj_err'], rtol=2e-5, atol=1e-4)       # pixels
+    np.testing.assert_allclose(err[:, 1], Gm['obj_err'], rtol=2e-5, atol=1e-6)
+    np.testing.assert_allclose(err[:, 2], Gm['obj_err_sym'], rtol=2e-5, atol=1e-6)
+    assert np.isnan(M.pose_errors(c['pts'], c['pr'], c['gt'], c['Ks'], symmetric=False).cpu().numpy()[:, 2]).all()
+    for scale in (1.0, 0.5):
+        for symmetric in (False, True):
+            got = M.compute_metrics_impl(c['pts'], c['diameter'], list(c['gt']), list(c['pr']), list(c['Ks']), scale, symmetric)
+            want = OM.compute_metrics_impl(c['pts'], c['diameter'], list(c['gt']), list(c['pr']), list(c['Ks']), scale, symmetric)
+            assert {k: float(v) for k, v in got.items()} == {k: float(v) for k, v in want.items()}
