@@ -218,16 +218,16 @@ def select_views_fps(database, ids, count):
 def select_views_near_pose(database, center, ids, pose, count=6, even=False, even_count=128):
     """database_utils.py:125-139: optionally re-spread with FPS, then the `count` views whose
     viewing direction is closest (largest cosine) to that of `pose`."""
+    unit = lambda v: v / np.linalg.norm(v, 2, -1, keepdims=True)
     if even and hasattr(database, 'even_subset'):
-        ids, poses = database.even_subset(ids, even_count)
+        ids, poses, dirs = database.even_subset(ids, even_count, center)     # pose-independent: cached per reference set
     else:
         ids = np.asarray(ids)
         poses = np.asarray([database.get_pose(i) for i in ids])
         if even:
             keep = farthest_point_indices(np.asarray([camera_center(p) for p in poses]), even_count + 1)
             ids, poses = ids[keep], poses[keep]
-    unit = lambda v: v / np.linalg.norm(v, 2, -1, keepdims=True)
-    dirs = unit(np.asarray([camera_center(p) for p in poses]) - center[None])
+        dirs = unit(np.asarray([camera_center(p) for p in poses]) - center[None])
     q = unit(camera_center(pose) - center)
     return ids[np.argsort(-(dirs @ q))[:count]]
 
@@ -254,26 +254,38 @@ def _project_center_batch(center, poses, Ks):
     return p[:, :2] / d[:, None]
 
 
-def normalize_reference_views(database, ids, size, margin, align_pose=None, align_K=None, warp=True):
-    """database_utils.py:54-110 (rectify_rot=True, no extra rotations): every reference view is
-    re-rendered as a look-at crop of the object at a common apparent size, with the in-plane
-    orientation either 'object-up' (build time) or aligned to a given pose (refinement).
-    Returns imgs [n,size,size,3] u8, Ks, poses, Hs (masks are not used on the inference path).
-    The camera algebra is batched over the views (float64); only the warps loop."""
+def reference_view_table(database, ids, size, margin):
+    """The part of normalize_reference_views that does not depend on the alignment pose, batched over
+    the views (float64): look-at rotation of every view, its product with the view's rotation, the
+    focal length of the normalised crop, K^-1."""
     center = database.object_center().astype(np.float64)
     diameter = database.object_diameter()
     poses = np.stack([database.get_pose(i) for i in ids], 0).astype(np.float64)
     Ks = np.stack([database.get_K(i) for i in ids], 0).astype(np.float64)
-    n = len(ids)
     cen_px = _project_center_batch(center, poses, Ks)
     cams = -np.einsum('nji,nj->ni', poses[:, :, :3], poses[:, :, 3])
     dist = np.linalg.norm(cams - center[None], axis=1)
     R_look, f_look = _look_at_batch(cen_px, Ks)
     scale = size * (1 - margin) / diameter * dist / f_look
+    return {'poses': poses, 'R_look': R_look, 'RlookR': R_look @ poses[:, :, :3], 'f': f_look * scale,
+            'Kinv': np.linalg.inv(Ks)}
+
+
+def normalize_reference_views(database, ids, size, margin, align_pose=None, align_K=None, warp=True):
+    """database_utils.py:54-110 (rectify_rot=True, no extra rotations): every reference view is
+    re-rendered as a look-at crop of the object at a common apparent size, with the in-plane
+    orientation either 'object-up' (build time) or aligned to a given pose (refinement).
+    Returns imgs [n,size,size,3] u8, Ks, poses, Hs (masks are not used on the inference path).
+    The camera algebra is batched over the views (float64); only the warps loop.  Databases that
+    offer `view_table` (NormalizedView) serve the pose-independent half from a per-object cache."""
+    tab = database.view_table(ids, size, margin) if hasattr(database, 'view_table') else reference_view_table(database, ids, size, margin)
+    poses, R_look = tab['poses'], tab['R_look']
+    n = len(ids)
     if align_pose is not None:
+        center = database.object_center().astype(np.float64)
         ap, aK = align_pose.astype(np.float64), align_K.astype(np.float64)
         Rq = look_at_point(ap, aK, center)[0] @ ap[:, :3]
-        rel = Rq[None] @ np.transpose(R_look @ poses[:, :, :3], (0, 2, 1))
+        rel = Rq[None] @ np.transpose(tab['RlookR'], (0, 2, 1))
         # R = Rx(c) Ry(b) Rz(a)  =>  first row = [cos b cos a, -cos b sin a, sin b]
         angle = np.arctan2(-rel[:, 0, 1], rel[:, 0, 0])
     else:
@@ -285,11 +297,10 @@ def normalize_reference_views(database, ids, size, margin, align_pose=None, alig
     z, o = np.zeros(n), np.ones(n)
     Rz = np.stack([np.stack([ca, -sa, z], -1), np.stack([sa, ca, z], -1), np.stack([z, z, o], -1)], 1).astype(np.float32)
     R = Rz @ R_look                                            # reference builds R_z in float32
-    f = f_look * scale
     K_new = np.zeros((n, 3, 3), np.float32)
-    K_new[:, 0, 0] = K_new[:, 1, 1] = f
+    K_new[:, 0, 0] = K_new[:, 1, 1] = tab['f']
     K_new[:, 0, 2], K_new[:, 1, 2], K_new[:, 2, 2] = size / 2, size / 2, 1
-    Hs = K_new @ R @ np.linalg.inv(Ks)
+    Hs = K_new @ R @ tab['Kinv']
     rect = R.astype(np.float32)
     poses_new = np.concatenate([rect @ poses[:, :, :3], rect @ poses[:, :, 3:]], 2)
     imgs = np.stack([cv2.warpPerspective(database.get_image(i), Hs[k], (size, size), flags=cv2.INTER_LINEAR)
@@ -333,6 +344,7 @@ class NormalizedView:
         self.offset = -self.scale * database.object_center()
         self._poses = {}        # normalised poses, cached (pose-independent of the query)
         self._even = {}         # FPS-resampled reference subsets per (ids, count)
+        self._tables = {}       # pose-independent halves of normalize_reference_views per (size, margin)
 
     def normalize_pose(self, pose):
         R, t = pose[:3, :3], pose[:3, 3]
@@ -347,16 +359,33 @@ class NormalizedView:
             self._poses[i] = self.normalize_pose(self.db.get_pose(i))
         return self._poses[i]
 
-    def even_subset(self, ids, count):
-        """The FPS re-spread of database_utils.py:129-134 depends only on the reference set, not on
-        the query pose: computed once per (ids, count) instead of once per refinement iteration."""
+    def even_subset(self, ids, count, center):
+        """The FPS re-spread of database_utils.py:129-134 and the unit viewing directions depend only
+        on the reference set, not on the query pose: computed once per (ids, count) instead of once
+        per refinement iteration."""
         key = (tuple(ids), count)
         if key not in self._even:
             ids_a = np.asarray(ids)
             poses = np.asarray([self.get_pose(i) for i in ids_a])
             keep = farthest_point_indices(np.asarray([camera_center(p) for p in poses]), count + 1)
-            self._even[key] = (ids_a[keep], poses[keep])
+            poses = poses[keep]
+            cams = np.asarray([camera_center(p) for p in poses]) - np.asarray(center)[None]
+            self._even[key] = (ids_a[keep], poses, cams / np.linalg.norm(cams, 2, -1, keepdims=True))
         return self._even[key]
+
+    def view_table(self, ids, size, margin, prefill=()):
+        """Rows of reference_view_table for `ids`, from a table built once per (size, margin) over the
+        reference set `prefill` (per-view quantities do not depend on which other views are in the batch)."""
+        key = (size, margin)
+        tab, index = self._tables.get(key, (None, {}))
+        missing = [i for i in ids if i not in index]
+        if missing:
+            all_ids = list(index) + [i for i in dict.fromkeys(list(prefill) + missing) if i not in index]
+            tab = reference_view_table(self, all_ids, size, margin)
+            index = {i: k for k, i in enumerate(all_ids)}
+            self._tables[key] = (tab, index)
+        rows = np.asarray([index[i] for i in ids])
+        return {k: v[rows] for k, v in tab.items()}
 
     def get_K(self, i):
         return self.db.get_K(i)
@@ -400,6 +429,7 @@ def refine_problem(database, ref_ids, que_img, que_K, in_pose, size=128, ref_num
     que_crop, K_warp, pose_warp, pose_rect, que_H = look_at_crop(que_img if warp else None, que_K, pose_n, cen_px, 0,
                                                                  scale, size, size)
     ids = select_views_near_pose(view, center, ref_ids, pose_warp, ref_num, ref_even, min(128, len(ref_ids)))
+    view.view_table(ids, size, margin, prefill=ref_ids)          # builds the per-object table on first use
     ref_imgs, ref_Ks, ref_poses, ref_Hs = normalize_reference_views(view, ids, size, margin, pose_warp, K_warp, warp)
     return {'view': view, 'que_img': que_crop, 'que_K': K_warp.astype(np.float32), 'que_H': que_H, 'ref_Hs': ref_Hs,
             'que_pose': pose_warp.astype(np.float32), 'pose_rect': pose_rect, 'center': center, 'ref_ids': ids,
