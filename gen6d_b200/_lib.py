@@ -15,6 +15,7 @@ HEADER_PATH = os.path.join(os.path.dirname(HERE), 'include', 'gen6d_b200.h')
 G6D_DET_MAX_SCALES = 8
 PRO_NONE, PRO_AFFINE, PRO_AFFINE_RELU, PRO_CORR = 0, 1, 2, 3
 ACT_NONE, ACT_RELU, ACT_LEAKY01 = 0, 1, 2
+TC_TF32, TC_F16 = 0, 1
 
 
 class ConvDesc(C.Structure):
@@ -51,13 +52,13 @@ _SIGNATURES = {
     'g6d_conv': [C.POINTER(ConvDesc), P, P, P, P, P, P, P, P],
     'g6d_conv_workspace_bytes': [C.POINTER(ConvDesc)],
     'g6d_pack_conv_weight': [P, P, I, I, I, I, P, P],
-    'g6d_conv_tc_supported': [C.POINTER(ConvDesc)],
+    'g6d_conv_tc_supported': [C.POINTER(ConvDesc), I],
     'g6d_conv_tc_debug': [C.POINTER(C.c_int)],
     'g6d_debug_umma_shift': [P, I, I, P],
-    'g6d_conv_tc_workspace_bytes': [C.POINTER(ConvDesc)],
-    'g6d_conv_tc': [C.POINTER(ConvDesc), P, P, P, P, I, P, P, P, P, P, P],
-    'g6d_pack_conv_weight_tc': [P, P, P, P, I, I, I, I, I, P, P],
-    'g6d_split_tf32': [P, P, P, L, P],
+    'g6d_conv_tc_workspace_bytes': [C.POINTER(ConvDesc), I],
+    'g6d_conv_tc': [C.POINTER(ConvDesc), P, P, P, I, I, P, P, P, P, P, P],
+    'g6d_pack_conv_weight_tc': [P, P, P, I, I, I, I, I, P, I, P],
+    'g6d_split_operand': [P, P, P, L, I, P],
     'g6d_transpose2d': [P, P, I, I, P],
     'g6d_linear_smallm': [P, P, P, P, I, I, I, I, P],
     'g6d_det_score_fuse': [C.POINTER(DetMaps), I, P, P, P, P, P, P],

@@ -111,11 +111,17 @@ __global__ void det_parse_kernel(const float* __restrict__ scores, const float* 
     const int qi = blockIdx.x;
     const int n = hs * ws;
     const float* sc = scores + (long long)qi * n;
-    // first-max argmax (torch.argmax returns the lowest index among ties, detector.py:91)
-    float bv = -INFINITY; int bi = 0x7fffffff;
+    // first-max argmax (torch.argmax returns the lowest index among ties and treats NaN as the
+    // maximum, detector.py:91): candidate (v, i) beats (bv, bi) under that order
+    auto beats = [](float v, int i, float bv, int bi) {
+        const bool vn = v != v, bn = bv != bv;
+        if (vn || bn) return vn && (!bn || i < bi);
+        return v > bv || (v == bv && i < bi);
+    };
+    float bv = -INFINITY; int bi = 0x7fffffff;      // sentinel: loses to every real element (even -inf) on the index
     for (int i = threadIdx.x; i < n; i += blockDim.x) {
         const float v = sc[i];
-        if (v > bv || (v == bv && i < bi)) { bv = v; bi = i; }
+        if (beats(v, i, bv, bi)) { bv = v; bi = i; }
     }
     __shared__ float sv[256]; __shared__ int si[256];
     sv[threadIdx.x] = bv; si[threadIdx.x] = bi;
@@ -123,12 +129,12 @@ __global__ void det_parse_kernel(const float* __restrict__ scores, const float* 
     for (int o = blockDim.x / 2; o > 0; o >>= 1) {
         if (threadIdx.x < o) {
             const float v = sv[threadIdx.x + o]; const int i = si[threadIdx.x + o];
-            if (v > sv[threadIdx.x] || (v == sv[threadIdx.x] && i < si[threadIdx.x])) { sv[threadIdx.x] = v; si[threadIdx.x] = i; }
+            if (beats(v, i, sv[threadIdx.x], si[threadIdx.x])) { sv[threadIdx.x] = v; si[threadIdx.x] = i; }
         }
         __syncthreads();
     }
     if (threadIdx.x == 0) {
-        const int idx = si[0];
+        const int idx = min(max(si[0], 0), n - 1);
         const int y = idx / ws, x = idx % ws;
         const float ox = offsets[((long long)qi * n + idx) * 2 + 0], oy = offsets[((long long)qi * n + idx) * 2 + 1];
         out[qi * 4 + 0] = ((float)x + ox + 0.5f) * (float)pool - 0.5f;

@@ -287,8 +287,8 @@ __global__ void sel_parse_kernel(const float* __restrict__ logits, const float* 
     const float* l = logits + (long long)qi * rfn;
     int best = 0;
     float bv = l[0];
-    for (int r = 1; r < rfn; ++r)
-        if (l[r] > bv) { bv = l[r]; best = r; }
+    for (int r = 1; r < rfn; ++r)      // first maximum; NaN counts as the maximum (torch.argmax, selector.py:172)
+        if (l[r] > bv || (l[r] != l[r] && bv == bv)) { bv = l[r]; best = r; }
     out_idx[qi] = best;
     out[qi * 2 + 0] = angles[(long long)qi * rfn + best];
     out[qi * 2 + 1] = bv;

@@ -54,6 +54,14 @@ class ReferenceDatabaseAdapter(ObjectDatabase):
     def object_vert(self): return self._v
 
 
+def as_object_database(db):
+    """`db` itself if it already offers the ObjectDatabase interface, else a ReferenceDatabaseAdapter
+    around it (a reference-repo BaseDatabase: CustomDatabase, LINEMOD, GenMOP ...)."""
+    if all(hasattr(db, m) for m in ('object_center', 'object_diameter', 'object_vert')):
+        return db
+    return ReferenceDatabaseAdapter(db)
+
+
 def _look_at(cam, up):
     z = -cam / np.linalg.norm(cam)
     x = np.cross(z, up)

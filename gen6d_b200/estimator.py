@@ -59,6 +59,9 @@ class Gen6DEstimator:
         look-at crops, make the 5 in-plane rotated copies, and load the three networks."""
         if split_type != 'all':
             raise NotImplementedError("only the 'all' split (reference ids = all database ids) is supported")
+        from .database import as_object_database
+        database = as_object_database(database)       # reference-repo databases are wrapped on the fly
+        self._drop_workers()                           # clones made for a previous object are stale now
         center, vert = database.object_center(), database.object_vert()
         ids_all = database.get_img_ids()
         ref_ids = G.select_views_fps(database, ids_all, self.cfg['ref_view_num'])
@@ -86,6 +89,7 @@ class Gen6DEstimator:
                          'center': center, 'ref_ids': ref_ids}
         if self.refiner is not None:
             self.refiner.load_ref_imgs(database, ids_all)
+        torch.cuda.current_stream().synchronize()      # reference state complete before any other stream reads it
 
     def predict(self, que_img, que_K, pose_init=None):
         """estimator.py:173-216.  que_img uint8 [h,w,3], que_K [3,3] -> (pose [3,4], inter_results)."""
@@ -126,9 +130,20 @@ class Gen6DEstimator:
     def worker_clone(self):
         import copy
         other = copy.copy(self)
+        other._workers, other._pool, other._workers_gen = None, None, None
         other.detector, other.selector = self.detector.worker_clone(), self.selector.worker_clone()
         other.refiner = self.refiner.worker_clone() if self.refiner is not None else None
         return other
+
+    def _generation(self):
+        mods = (self.detector, self.selector, self.refiner)
+        return tuple(m.generation for m in mods if m is not None)
+
+    def _drop_workers(self):
+        pool = getattr(self, '_pool', None)
+        if pool is not None:
+            pool.shutdown(wait=True)
+        self._workers, self._pool, self._workers_gen = None, None, None
 
     def predict_many(self, que_imgs, que_Ks, workers=2):
         """Poses for independent frames, `workers` frames in flight: each worker thread owns a clone
@@ -136,17 +151,24 @@ class Gen6DEstimator:
         stream, so one frame's host geometry (OpenCV warps, view selection) overlaps another frame's
         kernels.  Same per-frame computation and results as predict(); returns [(pose, inter)]."""
         from concurrent.futures import ThreadPoolExecutor
-        if not hasattr(self, '_workers') or len(self._workers) != workers:
+        # The clones share weights / reference features by reference and own captured graphs over them:
+        # rebuild them whenever any module's state changed (build() on another object, load_state_dict).
+        if getattr(self, '_workers', None) is None or len(self._workers) != workers or self._workers_gen != self._generation():
+            self._drop_workers()
             self._workers = [(self.worker_clone(), torch.cuda.Stream()) for _ in range(workers)]
+            self._workers_gen = self._generation()
             self._pool = ThreadPoolExecutor(workers)
             for est, stream in self._workers:        # capture every worker's stage graphs one at a time
+                stream.wait_stream(torch.cuda.current_stream())
                 with torch.cuda.stream(stream):
                     est.predict(que_imgs[0], que_Ks[0])
                     stream.synchronize()
         results = [None] * len(que_imgs)
+        caller = torch.cuda.current_stream()
 
         def run(w):
             est, stream = self._workers[w]
+            stream.wait_stream(caller)               # order after whatever the caller enqueued (uploads, a rebuild)
             with torch.cuda.stream(stream):
                 for i in range(w, len(que_imgs), workers):
                     results[i] = est.predict(que_imgs[i], que_Ks[i])

@@ -19,15 +19,22 @@ class PackedModule(nn.Module):
         self._packed = None
         self.stages = StageCache()      # CUDA graphs of the fixed-shape numpy-API stages
         self._pinned, self._pinned_next = {}, {}
+        self.generation = 0             # bumped whenever weights or cached reference state change (worker clones go stale)
         self.register_load_state_dict_post_hook(lambda module, keys: module.invalidate_packed())
+
+    def bump_generation(self):
+        """Called after anything a worker_clone() shares by reference was replaced: packed weights,
+        cached reference features.  Holders of clones (Gen6DEstimator.predict_many) compare it."""
+        self.generation += 1
+        self.stages.clear()             # captured graphs hold pointers into the previous state
 
     def invalidate_packed(self):
         self._packed = None
-        self.stages.clear()
+        self.bump_generation()
 
     def _apply(self, fn, *args, **kwargs):
         self._packed = None
-        self.stages.clear()
+        self.bump_generation()
         return super()._apply(fn, *args, **kwargs)
 
     @property
@@ -92,19 +99,25 @@ class Branches:
     Works eagerly and under CUDA-graph capture (the side streams fork from and join back into the
     capturing stream, so the captured graph gets parallel branches).  Branch results must be kept
     alive by the caller until they have been consumed on the main stream.  G6D_BRANCH_STREAMS=0
-    serialises everything on the current stream."""
+    serialises everything on the current stream.
+    The side streams are pooled per (device, main stream): host threads that drive different main
+    streams (predict_many workers) never share a side stream, so concurrent captures cannot fork the
+    same stream twice and the caching allocator never hands a block freed under one thread's side
+    stream to another thread's work on it."""
     _pool = {}
+    _pool_lock = __import__('threading').Lock()
 
     def __init__(self, n):
         import os
         self.enabled = os.environ.get('G6D_BRANCH_STREAMS', '1') != '0' and n > 1
         self.main = torch.cuda.current_stream()
         if self.enabled:
-            dev = torch.cuda.current_device()
-            pool = Branches._pool.setdefault(dev, [])
-            while len(pool) < n:
-                pool.append(torch.cuda.Stream())
-            self.streams = pool[:n]
+            key = (torch.cuda.current_device(), self.main.cuda_stream)
+            with Branches._pool_lock:
+                pool = Branches._pool.setdefault(key, [])
+                while len(pool) < n:
+                    pool.append(torch.cuda.Stream())
+                self.streams = pool[:n]
             for st in self.streams:
                 st.wait_stream(self.main)
 

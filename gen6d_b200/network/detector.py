@@ -59,11 +59,10 @@ class Detector(PackedModule):
             flat = f.reshape(rfn, k * k * c)
             pc = ops.PackedConv(ops.transpose_to_packed(flat), None, c, rfn, (1, k, k), 1, (0, k // 2, k // 2))
             if rfn >= 16:   # channels-last features [rfn, (ky,kx,c)] are already the K-major B operand
-                pc.w_hi, pc.w_lo = ops.split_tf32(flat)
-                pc.w_raw = flat
+                pc.w_hi, pc.w_lo, pc.kind = ops.split_operand(flat, ops.tc_kind_for(c))
             kernels.append(pc)
         self.ref_kernels = kernels
-        self.stages.clear()             # captured graphs hold pointers to the previous reference set
+        self.bump_generation()          # captured graphs / worker clones hold pointers to the previous reference set
 
     def scale_sizes(self, hq, wq):
         """detector.py:236-239: round(h * 2**s), rounded UP to a multiple of 32."""

@@ -4,7 +4,7 @@ The drop-in boundary includes checkpoint compatibility: a Gen6D
 `model_best.pth['network_state_dict']` must `load_state_dict` into our classes unchanged.  The
 modules below therefore only *hold* parameters under the reference's names -- their torch
 `forward` is never called; the compute runs through the C-ABI kernels on packed copies (see
-`packing.py`).  Layer tables are written as compact specs rather than literal module listings.
+`ops.pack_conv` and each network's `_pack`).  Layer tables are written as compact specs rather than literal module listings.
 
 Reference layouts mirrored: network/pretrain_models.py:86-111 (VGG11-BN 'A' features),
 network/detector.py:159-184, network/selector.py:27-111, network/attention.py:28-48,

@@ -176,9 +176,15 @@ class VolumeRefiner(PackedModule):
 
     # ------------------------------------------------------------------ reference numpy API
     def load_ref_imgs(self, ref_database, ref_ids):
-        self.ref_database = ref_database
+        """refiner.py:271-273.  `ref_database` may be one of this package's ObjectDatabase objects or a
+        database of the reference repo (dataset/database.py BaseDatabase), exactly as the reference's
+        estimator.py:171 passes it: the latter is wrapped on the fly (the reference reads the object's
+        centre / diameter / up vector through free functions, database.py:311-397)."""
+        from ..database import as_object_database
+        self.ref_database = as_object_database(ref_database)
         self.ref_ids = ref_ids
         self._ref_dev = {}          # image id -> device uint8 [rows, cols, 3] (filled on first use)
+        self.bump_generation()
 
     def _ref_images_dev(self, ids):
         """The database images the look-at crops are cut from, resident on the device: all of them

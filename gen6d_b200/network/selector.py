@@ -132,7 +132,7 @@ class ViewpointSelector(PackedModule):
         for i, pc in enumerate(p['vpe']):
             x = ops.conv(x, pc, act=ops.ACT_RELU if i < 2 else ops.ACT_NONE)
         self.ref_pose_embed = x.reshape(rfn, 512)
-        self.stages.clear()             # captured graphs hold pointers to the previous reference set
+        self.bump_generation()          # captured graphs / worker clones hold pointers to the previous reference set
 
     def _stats(self, y, rows_local, rows_total):
         """InstanceNorm statistics over a group that may span GPUs: local (sum, sum-of-squares) in

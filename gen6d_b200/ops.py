@@ -221,14 +221,31 @@ class PackedConv:
     k: tuple          # (kd, kh, kw)
     stride: int = 1
     pad: tuple = (0, 0, 0)
-    w_hi: Optional[torch.Tensor] = None   # tensor-core path: [rows, K] tf32 hi / lo split (K-major)
+    w_hi: Optional[torch.Tensor] = None   # tensor-core path: [rows, K] hi / lo operand split (K-major)
     w_lo: Optional[torch.Tensor] = None
-    w_raw: Optional[torch.Tensor] = None  # the same matrix unsplit (G6D_CONV_TC_V=4 kernel splits it in shared memory)
+    kind: int = _lib.TC_TF32              # container of w_hi / w_lo: TC_TF32 (fp32 arrays) or TC_F16 (half arrays)
 
 
 def conv_path():
-    """'tc' (tcgen05 3xTF32, default) or 'ffma' (fp32 CUDA-core fallback for A/B checks): env G6D_CONV_PATH."""
+    """'tc' (tcgen05 split-operand kernels, default) or 'ffma' (fp32 CUDA-core fallback for A/B checks): env G6D_CONV_PATH."""
     return os.environ.get('G6D_CONV_PATH', 'tc')
+
+
+def conv_kind():
+    """Operand kind of the tensor-core path, env G6D_CONV_KIND: 'f16' (default; fp16 hi + 2^11-scaled fp16
+    lo halves, kind::f16 MMAs: twice the K per instruction and per byte) or 'tf32' (tf32 halves: any fp32 range)."""
+    return _lib.TC_TF32 if os.environ.get('G6D_CONV_KIND', 'f16') == 'tf32' else _lib.TC_F16
+
+
+def tc_kind_for(cin_pad):
+    """The kind a layer with `cin_pad` input channels is packed for (None: not tensor-core eligible)."""
+    if cin_pad % 64 == 0 and conv_kind() == _lib.TC_F16:
+        return _lib.TC_F16
+    return _lib.TC_TF32 if cin_pad % 32 == 0 else None
+
+
+def _tc_dtype(kind):
+    return torch.float16 if kind == _lib.TC_F16 else torch.float32
 
 
 def pack_conv(weight, bias=None, stride=1, pad=None, cin_pad=None, cout_scale=None, bias_override=None):
@@ -252,20 +269,25 @@ def pack_conv(weight, bias=None, stride=1, pad=None, cin_pad=None, cout_scale=No
     b = bias_override if bias_override is not None else bias
     b = b.detach().to(torch.float32).contiguous() if b is not None else None
     pc = PackedConv(out, b, cin_pad, cout, k3, stride, pad)
-    if cin_pad % 32 == 0 and cout >= 16:
+    kind = tc_kind_for(cin_pad)
+    if kind is not None and cout >= 16:
         rows = (cout + 7) // 8 * 8
-        pc.w_hi = torch.empty(rows, taps * cin_pad, device=w.device, dtype=torch.float32)
+        pc.kind = kind
+        pc.w_hi = torch.empty(rows, taps * cin_pad, device=w.device, dtype=_tc_dtype(kind))
         pc.w_lo = torch.empty_like(pc.w_hi)
-        pc.w_raw = torch.empty_like(pc.w_hi)
-        _call('g6d_pack_conv_weight_tc', _p(w), _p(pc.w_hi), _p(pc.w_lo), _p(pc.w_raw), cout, cin, cin_pad, taps, rows,
-              _p(cout_scale.contiguous()) if cout_scale is not None else None, _stream())
+        _call('g6d_pack_conv_weight_tc', _p(w), _p(pc.w_hi, pc.w_hi.dtype), _p(pc.w_lo, pc.w_lo.dtype), cout, cin, cin_pad,
+              taps, rows, _p(cout_scale.contiguous()) if cout_scale is not None else None, kind, _stream())
     return pc
 
 
-def split_tf32(x):
-    hi, lo = torch.empty_like(x), torch.empty_like(x)
-    _call('g6d_split_tf32', _p(x), _p(hi), _p(lo), x.numel(), _stream())
-    return hi, lo
+def split_operand(x, kind=None):
+    """fp32 [rows, K] -> (hi, lo, kind): the K-major B operand of the tensor-core path (detector
+    reference features used as correlation kernels)."""
+    kind = tc_kind_for(x.shape[-1]) if kind is None else kind
+    hi = torch.empty(x.shape, device=x.device, dtype=_tc_dtype(kind))
+    lo = torch.empty_like(hi)
+    _call('g6d_split_operand', _p(x), _p(hi, hi.dtype), _p(lo, lo.dtype), x.numel(), kind, _stream())
+    return hi, lo, kind
 
 
 def transpose_to_packed(x2d):
@@ -296,13 +318,13 @@ def conv(x, pc, prologue=PRO_NONE, pro_scale=None, pro_shift=None, group_rows=1,
                       kw=kw, stride=s, pd=pd, ph=ph, pw=pw, Do=Do, Ho=Ho, Wo=Wo, out_cstride=out.shape[-1],
                       out_coff=out_coff, prologue=prologue, group_rows=group_rows, act=act)
     work = 2.0 * B * Do * Ho * Wo * pc.cout * kd * kh * kw * pc.cin
-    if pc.w_hi is not None and conv_path() == 'tc' and _lib.lib().g6d_conv_tc_supported(C.byref(d)):
-        nbytes = _lib.lib().g6d_conv_tc_workspace_bytes(C.byref(d))
+    if pc.w_hi is not None and conv_path() == 'tc' and _lib.lib().g6d_conv_tc_supported(C.byref(d), pc.kind):
+        nbytes = _lib.lib().g6d_conv_tc_workspace_bytes(C.byref(d), pc.kind)
         if nbytes < 0:
             _lib.check(-1, 'g6d_conv_tc_workspace_bytes')
         ws = torch.empty(nbytes // 4, device=x.device, dtype=torch.float32) if nbytes > 0 else None
-        _call('g6d_conv_tc', C.byref(d), _p(x), _p(pc.w_hi), _p(pc.w_lo), _p(pc.w_raw), pc.w_hi.shape[0], _p(pc.bias), _p(pro_scale),
-              _p(pro_shift), _p(out), _p(ws), _stream(), work=work,
+        _call('g6d_conv_tc', C.byref(d), _p(x), _p(pc.w_hi, pc.w_hi.dtype), _p(pc.w_lo, pc.w_lo.dtype), pc.w_hi.shape[0],
+              pc.kind, _p(pc.bias), _p(pro_scale), _p(pro_shift), _p(out), _p(ws), _stream(), work=work,
               tag=f'M={B * Do * Ho * Wo} N={pc.cout} K={kd * kh * kw * pc.cin} k={kd}x{kh}x{kw} s={s} pro={prologue}')
         return out
     nbytes = _lib.lib().g6d_conv_workspace_bytes(C.byref(d))

@@ -149,29 +149,33 @@ long long g6d_conv_workspace_bytes(const g6d_conv_desc* desc);
  * (eval-mode BatchNorm fold). */
 int g6d_pack_conv_weight(const float* w, float* out, int Cout, int Cin, int Cin_pad, int taps,
                          const float* cout_scale, g6d_stream_t stream);
-/* ---- tensor-core path (tcgen05, 3xTF32 split: fp32-faithful on the tensor pipe) -------------
- * Same contract as g6d_conv, for problems with Cin % 32 == 0 and Cout >= 16
- * (g6d_conv_tc_supported).  Weights are pre-split [w_rows >= Cout, K] K-major arrays
- * (K = tap*Cin + c): w_hi = tf32(w), w_lo = tf32(w - w_hi), see g6d_pack_conv_weight_tc /
- * g6d_split_tf32.  w_raw (optional, may be NULL) is the same matrix unsplit: the G6D_CONV_TC_V=4
- * kernel streams only it and derives the lo half in shared memory (half the weight traffic).
- * A tiles are gathered + transformed by producer warps, B tiles arrive by TMA, accumulators live
- * in TMEM. */
-int g6d_conv_tc_supported(const g6d_conv_desc* desc);
+/* ---- tensor-core path (tcgen05, three-term operand split: fp32-faithful on the tensor pipe) ------
+ * Same contract as g6d_conv, for problems g6d_conv_tc_supported accepts (Cin a multiple of the
+ * kind's K-block, Cout >= 16).  A*B ~= A_hi*B_hi + A_hi*B_lo + A_lo*B_hi with 11-bit-significand
+ * halves; `kind` selects their container:
+ *   G6D_TC_TF32: hi = tf32(x), lo = tf32(x - hi), fp32 arrays, K-block 32, tcgen05.mma kind::tf32;
+ *   G6D_TC_F16 : hi = fp16(x), lo = fp16((x - hi) * 2^11), __half arrays, K-block 64, kind::f16 (twice
+ *                the K per instruction and per operand byte; the kernels undo the 2^11 in the epilogue).
+ *                Range contract: |x| <= 65504 (saturating), full accuracy for |x| >= 6.1e-5.
+ * Weights are pre-split [w_rows >= Cout, K] K-major arrays (K = tap*Cin + c), see
+ * g6d_pack_conv_weight_tc / g6d_split_operand.  A tiles are gathered + transformed + split by
+ * producer warps, B tiles arrive by TMA, accumulators live in TMEM. */
+#define G6D_TC_TF32 0
+#define G6D_TC_F16 1
+int g6d_conv_tc_supported(const g6d_conv_desc* desc, int kind);
 /* debug probe: D[128x32] = A[shift..shift+128) x I for a row-shifted SWIZZLE_128B descriptor (mode: base_offset rule) */
 int g6d_debug_umma_shift(float* out, int shift, int mode, g6d_stream_t stream);
 /* debug: host_out8[0] != 0 if a pipeline wait inside g6d_conv_tc timed out (kernel bailed out); syncs */
 int g6d_conv_tc_debug(int* host_out8);
-long long g6d_conv_tc_workspace_bytes(const g6d_conv_desc* desc);
-int g6d_conv_tc(const g6d_conv_desc* desc, const float* x, const float* w_hi, const float* w_lo,
-                const float* w_raw, int w_rows, const float* bias, const float* pro_scale, const float* pro_shift, float* y, void* ws,
+long long g6d_conv_tc_workspace_bytes(const g6d_conv_desc* desc, int kind);
+int g6d_conv_tc(const g6d_conv_desc* desc, const float* x, const void* w_hi, const void* w_lo, int w_rows, int kind,
+                const float* bias, const float* pro_scale, const float* pro_shift, float* y, void* ws,
                 g6d_stream_t stream);
-/* [Cout, Cin, taps] (reference layout) -> hi/lo (and, if out_raw != NULL, unsplit) [rows_pad, taps*Cin_pad];
- * optional BN-fold scale */
-int g6d_pack_conv_weight_tc(const float* w, float* out_hi, float* out_lo, float* out_raw, int Cout, int Cin, int Cin_pad, int taps,
-                            int rows_pad, const float* cout_scale, g6d_stream_t stream);
-/* hi = tf32(x), lo = tf32(x - hi), elementwise (detector reference features as kernels) */
-int g6d_split_tf32(const float* in, float* hi, float* lo, long long n, g6d_stream_t stream);
+/* [Cout, Cin, taps] (reference layout) -> hi/lo [rows_pad, taps*Cin_pad] of the given kind; optional BN-fold scale */
+int g6d_pack_conv_weight_tc(const float* w, void* out_hi, void* out_lo, int Cout, int Cin, int Cin_pad, int taps,
+                            int rows_pad, const float* cout_scale, int kind, g6d_stream_t stream);
+/* elementwise hi/lo split of an fp32 array into the given kind (detector reference features as kernels) */
+int g6d_split_operand(const float* in, void* hi, void* lo, long long n, int kind, g6d_stream_t stream);
 /* [rows, K] row-major -> [K, rows] (detector reference features [rfn,k,k,512] -> correlation kernels) */
 int g6d_transpose2d(const float* in, float* out, int rows, int cols, g6d_stream_t stream);
 /* y[m, n] = act(sum_k x[m,k] w[n,k] + b[n]) for small m (<= 8): weight-bandwidth bound

@@ -76,6 +76,12 @@ def detector_case(seed=11, rfn=4, hq=96, wq=128, qn=1):
             'cfg': {'vgg_score_stats': DET_STATS}}
 
 
+def detector_case_full(seed=111):
+    """BASELINE configs[1], detector half: 480x640 frame, 32 reference views (the estimator default):
+    rfn >= 16 routes the correlation through the tcgen05 kernel."""
+    return detector_case(seed=seed, rfn=32, hq=480, wq=640)
+
+
 def selector_case(seed=21, rfn=8, an=5, qn=1):
     poses = sphere_poses(seed + 2, rfn)
     return {'ref_imgs': rand_images_u8(seed, an, rfn, 128, 128, 3),
@@ -105,6 +111,12 @@ DET_STATS_EST = _syn.DET_SCORE_STATS
 
 def estimator_case():
     return {'db': dict(_syn.DATABASE), 'net_cfg': {}, 'query_id': '11'}
+
+
+def add_frame_ids(db, n=20):
+    """The frames of the ADD-0.1d acceptance run: every third view of the synthetic database, n of them."""
+    ids = db.get_img_ids()
+    return [ids[(3 * i + 1) % len(ids)] for i in range(n)]
 
 
 def metrics_case(n_pts=700, n_poses=14, seed=77):

@@ -67,8 +67,11 @@ def mat2quat(mat):
     return np.array([w, x, y, z])
 
 
-def install():
-    """Put stub modules in sys.modules, neutralise .cuda(), patch the VGG download."""
+def install(networks=True):
+    """Put stub modules in sys.modules, neutralise .cuda(), patch the VGG download.
+    networks=False: only the stubs for the absent third-party packages (the reference's own `network`
+    package is not imported and torch is left untouched) -- used by tests/test_dropin.py, which puts
+    gen6d_b200.network in its place."""
     if REFERENCE_ROOT not in sys.path:
         sys.path.insert(0, REFERENCE_ROOT)
 
@@ -87,6 +90,8 @@ def install():
     t3.quaternions = mod('transforms3d.quaternions', quat2mat=quat2mat, mat2quat=mat2quat)
     t3.axangles = mod('transforms3d.axangles', mat2axangle=mat2axangle)
 
+    if not networks:
+        return
     import torch
     import torchvision
     torch.Tensor.cuda = lambda self, *a, **k: self

@@ -32,32 +32,33 @@ def test_config1_selector_32refs_12bins():
     logits, angles = O.sel_forward(sd, cases.u8_to_nchw(c['que_imgs']), feats, embed)
     res = net.select_que_imgs(c['que_imgs'])
     top2 = torch.topk(logits, 2, 1)[0]
-    print('config-1 selector margin', float(top2[0, 0] - top2[0, 1]))
-    np.testing.assert_allclose(res['scores'], logits.numpy(), atol=4e-3)
+    margin = float(top2[0, 0] - top2[0, 1])
+    print('config-1 selector margin (oracle top-1 minus top-2):', margin)
+    assert margin > 0.2                      # seed 51 was chosen for a clear margin (0.24): the index check below is meaningful
+    np.testing.assert_allclose(res['scores'], logits.numpy(), atol=5e-4)
     idx, ang = O.sel_select(logits, angles)
-    if float(top2[0, 0] - top2[0, 1]) > 2e-2:
-        assert res['ref_idx'].tolist() == idx.tolist()
-    np.testing.assert_allclose(res['angles'], angles.numpy()[np.arange(1), res['ref_idx']], atol=4e-3)
+    assert res['ref_idx'].tolist() == idx.tolist()                              # bit-exact viewpoint, unconditionally
+    np.testing.assert_allclose(res['angles'], angles.numpy()[np.arange(1), res['ref_idx']], atol=5e-4)
 
 
 def test_detector_64refs_batch2_odd_size():
     """64 reference views (two lanes-per-ref passes in the fused head), qn = 2, frame 104x136."""
-    c = cases.detector_case(seed=61, rfn=64, hq=104, wq=136, qn=2)
+    c = cases.detector_case(seed=63, rfn=64, hq=104, wq=136, qn=2)      # seed 63: oracle margins 0.17 / 0.13 on the two frames
     net, sd = build('detector', {'name': 'd', 'network': 'detector', **c['cfg']})
     net.load_ref_imgs(c['ref_imgs'])
     ref_feats = O.det_load_refs(sd, cases.u8_to_nchw(c['ref_imgs']))
     want = O.det_detect(sd, c['cfg'], cases.u8_to_nchw(c['que_imgs']), ref_feats)
     got = net.detect_impl(cases.u8_to_nchw(c['que_imgs']).cuda())
-    np.testing.assert_allclose(got['scores'].cpu().numpy(), want['scores'].numpy(), atol=3e-3)
+    np.testing.assert_allclose(got['scores'].cpu().numpy(), want['scores'].numpy(), atol=5e-4)
     pos, scl, idx = O.det_parse(want['scores'], want['select_pr_scale'], want['select_pr_offset'])
     top2 = torch.topk(want['scores'].flatten(1), 2, 1)[0]
     margins = (top2[:, 0] - top2[:, 1]).tolist()
     print('detector margins', margins)
     ws = want['scores'].shape[-1]
     sel = got['que_select_id'].cpu()
-    for qi, mg in enumerate(margins):
-        if mg > 1e-2:
-            assert int(sel[qi, 1] * ws + sel[qi, 0]) == int(idx[qi])
+    assert min(margins) > 0.1
+    for qi in range(len(margins)):
+        assert int(sel[qi, 1] * ws + sel[qi, 0]) == int(idx[qi])               # bit-exact detection cell, both frames
     res = net.detect_que_imgs(c['que_imgs'])
     np.testing.assert_allclose(res['scales'], scl.numpy(), rtol=3e-3)
 
@@ -77,9 +78,9 @@ def test_refiner_batches(qn):
             'ref_imgs_info': {'imgs': cases.u8_to_nchw(c['ref_imgs']).cuda(), 'Ks': T(c['ref_Ks']).cuda(),
                               'poses': T(c['ref_poses']).cuda()}, 'inference': True}
     res = net(data)
-    np.testing.assert_allclose(res['rotation'][:n_or].cpu().numpy(), want['rotation'].numpy(), atol=2e-3)
-    np.testing.assert_allclose(res['offset'][:n_or].cpu().numpy(), want['offset'].numpy(), atol=2e-3)
-    np.testing.assert_allclose(res['scale'][:n_or].cpu().numpy(), want['scale'].numpy(), atol=2e-3)
+    np.testing.assert_allclose(res['rotation'][:n_or].cpu().numpy(), want['rotation'].numpy(), atol=3e-4)
+    np.testing.assert_allclose(res['offset'][:n_or].cpu().numpy(), want['offset'].numpy(), atol=3e-4)
+    np.testing.assert_allclose(res['scale'][:n_or].cpu().numpy(), want['scale'].numpy(), atol=3e-4)
     # poses are independent (per-sample InstanceNorm): a batch must equal its members run alone
     one = {k: ({kk: vv[qn - 1:qn] for kk, vv in v.items()} if isinstance(v, dict) else v) for k, v in data.items()}
     alone = net(one)
@@ -112,10 +113,12 @@ def test_config4_angle_bins_36():
                                    torch.from_numpy(c['object_center']), torch.from_numpy(c['object_vert']))
     logits, angles = O.sel_forward(sd, cases.u8_to_nchw(c['que_imgs']), feats, embed)
     res = net.select_que_imgs(c['que_imgs'])
-    np.testing.assert_allclose(res['scores'], logits.numpy(), atol=4e-3)
+    np.testing.assert_allclose(res['scores'], logits.numpy(), atol=5e-4)
     top2 = torch.topk(logits, 2, 1)[0]
-    if float(top2[0, 0] - top2[0, 1]) > 2e-2:
-        assert res['ref_idx'].tolist() == torch.argmax(logits, 1).tolist()
+    margin = float(top2[0, 0] - top2[0, 1])
+    print('36-bin selector margin (oracle):', margin)
+    assert margin > 1.0                      # seed 81: 1.69
+    assert res['ref_idx'].tolist() == torch.argmax(logits, 1).tolist()          # bit-exact viewpoint, unconditionally
 
 
 def test_config5_refiner_batch32_is_poses_independent():

@@ -1,5 +1,6 @@
-"""The tcgen05 3xTF32 convolution (g6d_conv_tc) against torch fp32 CPU and against the FFMA
-path: it must be fp32-faithful (error ~1e-6 relative, not TF32's 1e-3)."""
+"""The tcgen05 split-operand convolution (g6d_conv_tc) against torch fp64 CPU and against the FFMA
+path, for both operand kinds (G6D_TC_F16: fp16 hi + 2^11-scaled fp16 lo, the default; G6D_TC_TF32: tf32
+hi/lo): it must be fp32-faithful (error ~1e-6 relative; a single TF32 or fp16 product would be ~5e-4)."""
 import os
 
 import numpy as np
@@ -33,19 +34,32 @@ def ops():
     return ops
 
 
+@pytest.fixture(params=['f16', 'tf32'], autouse=True)
+def kind(request):
+    """Every test runs once per operand kind (read by ops.pack_conv / ops.split_operand at pack time)."""
+    old = os.environ.get('G6D_CONV_KIND')
+    os.environ['G6D_CONV_KIND'] = request.param
+    yield request.param
+    if old is None:
+        os.environ.pop('G6D_CONV_KIND', None)
+    else:
+        os.environ['G6D_CONV_KIND'] = old
+
+
 def rel_err(a, b):
     return float((a - b).abs().max() / b.abs().max())
 
 
 @pytest.mark.parametrize('B,H,W,cin,cout', [(1, 16, 16, 32, 32), (2, 17, 23, 64, 64), (1, 32, 40, 128, 256),
                                             (3, 8, 8, 512, 48), (1, 60, 80, 64, 128), (5, 4, 4, 256, 256)])
-def test_tc_conv2d_matches_fp32(ops, B, H, W, cin, cout):
+def test_tc_conv2d_matches_fp32(ops, kind, B, H, W, cin, cout):
     x = torch.randn(B, cin, H, W, generator=g(1)) + 0.5
     w = torch.randn(cout, cin, 3, 3, generator=g(2)) * (2 / (9 * cin)) ** .5
     b = torch.randn(cout, generator=g(3))
     ref = F.relu(F.conv2d(x.double(), w.double(), b.double(), padding=1)).float()
     pc = ops.pack_conv(w.cuda(), b.cuda(), pad=1)
     assert pc.w_hi is not None
+    assert pc.kind == (1 if (kind == 'f16' and cin % 64 == 0) else 0)
     os.environ['G6D_CONV_PATH'] = 'tc'
     y_tc = nchw(ops.conv(nhwc(x), pc, act=ops.ACT_RELU))
     os.environ['G6D_CONV_PATH'] = 'ffma'
@@ -74,7 +88,7 @@ def test_tc_splitk_correlation(ops):
     rk = r.permute(0, 2, 3, 1).contiguous().cuda()
     flat = rk.reshape(32, -1)
     pc = ops.PackedConv(ops.transpose_to_packed(flat), None, 512, 32, (1, 15, 15), 1, (0, 7, 7))
-    pc.w_hi, pc.w_lo = ops.split_tf32(flat)
+    pc.w_hi, pc.w_lo, pc.kind = ops.split_operand(flat, ops.tc_kind_for(512))
     y = nchw(ops.conv(nhwc(q), pc))
     assert rel_err(y, ref) < 5e-6
 
@@ -108,3 +122,26 @@ def test_tc_corr_prologue_and_channel_offsets(ops):
              pro_shift=shift.cuda(), group_rows=S, out=out, out_coff=64)
     assert rel_err(nchw(out[..., 64:128].contiguous()), ref) < 5e-6
     assert float(out[..., :64].abs().max()) == 0 and float(out[..., 128:].abs().max()) == 0
+
+
+@pytest.mark.parametrize('gain', [1e-3, 1.0, 3e2])
+def test_tc_dynamic_range(ops, kind, gain):
+    """Activations x gain, weights / gain: the fp16 kind keeps fp32-level accuracy over the range the
+    network's tensor-core operands live in (BN-folded weights, post-ReLU / normalised activations)."""
+    x = (torch.randn(1, 128, 24, 24, generator=g(30)).abs() * gain)
+    w = torch.randn(64, 128, 3, 3, generator=g(31)) * (2 / (9 * 128)) ** .5 / gain
+    ref = F.conv2d(x.double(), w.double(), None, padding=1).float()
+    y = nchw(ops.conv(nhwc(x), ops.pack_conv(w.cuda(), None, pad=1)))
+    e = rel_err(y, ref)
+    print(f'{kind} gain {gain:g}: rel err vs fp64 {e:.2e}')
+    assert e < 5e-6
+
+
+def test_tc_f16_saturates_instead_of_overflowing(ops, kind):
+    """Beyond the fp16 range the conversion saturates (finite result, large error) -- never inf / NaN."""
+    x = torch.full((1, 64, 8, 8), 1e6)
+    w = torch.full((32, 64, 1, 1), 1e-3)
+    y = ops.conv(nhwc(x), ops.pack_conv(w.cuda(), None, pad=0))
+    assert torch.isfinite(y).all()
+    if kind == 'tf32':
+        assert rel_err(nchw(y), torch.full((1, 32, 8, 8), 64e3)) < 1e-5

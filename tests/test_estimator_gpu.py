@@ -35,15 +35,21 @@ def test_predict_matches_reference(est):
     np.testing.assert_allclose(inter['det_scale_r2q'], E['est.det_scale'], rtol=5e-3)
     assert int(inter['sel_ref_idx']) == int(E['est.sel_ref_idx'])                               # bit-exact viewpoint
     np.testing.assert_allclose(inter['sel_angle_r2q'], E['est.sel_angle'], atol=2e-2)
-    # The pose handed to the refiner (detection + selection + similarity->pose) must agree.  The
-    # refined poses of THIS chain are not compared: with random weights the detector's scale is
-    # ~0.07, the implied object distance is ~40x off, the refiner then looks at featureless
-    # background and its InstanceNorms (1/sqrt(var + 1e-5) on near-constant channels) amplify fp32
-    # summation-order noise without bound.  Refinement parity is checked on a well-posed input in
-    # test_tracking_refinement_matches_reference and at tensor level in test_networks_gpu.py.
-    got, want = inter['refine_poses'][0], E['est.refine_poses'][0]
-    np.testing.assert_allclose(got[:, :3], want[:, :3], atol=5e-3)
-    np.testing.assert_allclose(got[:, 3], want[:, 3], rtol=5e-3, atol=5e-2)
+    # The whole chain: the pose handed to the refiner (detection + selection + similarity->pose), the
+    # pose after each of the three refinement iterations and the returned pose, against the golden
+    # run of the unmodified reference (est.det_scale = 0.93: the seeded heads keep the chain well-posed).
+    got, want = np.stack(inter['refine_poses'], 0), E['est.refine_poses']
+    assert got.shape == want.shape == (4, 3, 4)
+    err_r = np.abs(got[:, :, :3] - want[:, :, :3]).reshape(len(got), -1).max(1)
+    err_t = np.abs(got[:, :, 3] - want[:, :, 3]).max(1) / np.linalg.norm(want[:, :, 3], axis=1)
+    print('full chain, per-iteration max |dR|', err_r, 'relative |dt|', err_t)
+    np.testing.assert_allclose(got[0][:, :3], want[0][:, :3], atol=5e-3)
+    np.testing.assert_allclose(got[0][:, 3], want[0][:, 3], rtol=5e-3, atol=5e-2)
+    np.testing.assert_allclose(got[:, :, :3], want[:, :, :3], atol=1e-2)
+    assert (err_t < 1e-2).all()
+    np.testing.assert_allclose(pose[:, :3], E['est.pose'][:, :3], atol=1e-2)
+    np.testing.assert_allclose(pose[:, 3], E['est.pose'][:, 3], rtol=1e-2, atol=5e-2)
+    np.testing.assert_array_equal(pose, inter['refine_poses'][-1])
 
 
 def test_tracking_refinement_matches_reference(est):
@@ -68,3 +74,53 @@ def test_predict_many_equals_predict(est):
     par = e.predict_many(imgs, Ks, workers=2)
     for a, (b, _) in zip(seq, par):
         np.testing.assert_allclose(a, b, atol=1e-5)
+
+
+def test_device_build_equals_host_build(est):
+    """Gen6DEstimator.build with cfg['device_build'] cuts the same reference crops as the OpenCV path (row f2)."""
+    from gen6d_b200.synthetic import build_estimator
+    host, _ = est
+    dev, _ = build_estimator(device_build=True)
+    np.testing.assert_array_equal(dev.ref_info['imgs'], host.ref_info['imgs'])
+    np.testing.assert_array_equal(dev.ref_info['ref_imgs'], host.ref_info['ref_imgs'])
+
+
+def test_add_and_prj_match_reference_over_20_frames(est):
+    """north_star acceptance: "matched ADD-0.1d on synthetic inputs".  20 frames through predict(); the
+    per-frame ADD / projection errors (g6d_pose_errors, row f4) and the ADD-0.1d / Prj-5 rates against the
+    database's ground truth must equal those of the poses the unmodified reference estimator produced
+    (tests/golden/make_golden_add.py -> add_golden.npz, scored by the reference's utils/pose_utils.py:149-215)."""
+    from gen6d_b200 import metrics as M
+    e, db = est
+    A = np.load(os.path.join(HERE, 'golden', 'add_golden.npz'))
+    ids = [str(int(i)) for i in A['frame_ids']]
+    assert ids == cases.add_frame_ids(db)
+    poses, sel = [], []
+    for fid in ids:
+        pose, inter = e.predict(db.get_image(fid), db.get_K(fid))
+        poses.append(pose)
+        sel.append(int(inter['sel_ref_idx']))
+    poses = np.stack(poses, 0)
+    print('reference selector margins', A['sel_margin'])
+    assert sel == A['sel_ref_idx'].tolist()                                     # bit-exact viewpoints, every frame
+    pts, diameter = db.object_point_cloud.astype(np.float32), float(A['diameter'])
+    assert diameter == db.object_diameter()
+    # the reference's own poses through our metric kernel reproduce the reference's metric values ...
+    err_ref = M.pose_errors(pts, A['poses_pr'], A['poses_gt'], A['Ks']).cpu().numpy()
+    np.testing.assert_allclose(err_ref[:, 0], A['prj_err'], rtol=1e-4)
+    np.testing.assert_allclose(err_ref[:, 1], A['obj_err'], rtol=1e-4)
+    # ... and our poses score the same, frame by frame and in the rates
+    err = M.pose_errors(pts, poses, A['poses_gt'], A['Ks']).cpu().numpy()
+    d_add = np.abs(err[:, 1] - A['obj_err']) / (0.1 * diameter)
+    d_prj = np.abs(err[:, 0] - A['prj_err'])
+    print('per-frame |dADD| / 0.1d', d_add.round(4), '|dPrj| px', d_prj.round(3))
+    assert d_add.max() < 0.05 and (d_prj / A['prj_err']).max() < 0.02
+    got = M.compute_metrics_impl(pts, diameter, list(A['poses_gt']), list(poses), list(A['Ks']))
+    assert float(got['add-0.1d']) == float(A['res.add-0.1d']) and float(got['prj-5']) == float(A['res.prj-5'])
+    # the thresholds are not vacuous for this kernel: ground-truth poses score 100 %, and the reference's
+    # per-frame pass/fail pattern at a loose threshold is reproduced exactly
+    perfect = M.compute_metrics_impl(pts, diameter, list(A['poses_gt']), list(A['poses_gt']), list(A['Ks']))
+    assert float(perfect['add-0.1d']) == 1.0 and float(perfect['prj-5']) == 1.0
+    thr = float(np.median(A['obj_err']))
+    clear = np.abs(A['obj_err'] - thr) > 0.05 * 0.1 * diameter          # frames not within 5 % of 0.1 d of the threshold
+    assert ((err[:, 1] < thr) == (A['obj_err'] < thr))[clear].all()

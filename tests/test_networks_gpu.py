@@ -73,9 +73,9 @@ def test_detector_maps_argmax_positions(det):
     c, net, sd, ref_feats = det
     want = O.det_detect(sd, c['cfg'], cases.u8_to_nchw(c['que_imgs']), ref_feats)
     got = net.detect_impl(cases.u8_to_nchw(c['que_imgs']).cuda())
-    close(got['scores'], want['scores'], atol=2e-3)
-    close(got['select_pr_offset'], want['select_pr_offset'], atol=2e-3)
-    close(got['select_pr_scale'], want['select_pr_scale'], atol=2e-3)
+    close(got['scores'], want['scores'], atol=3e-4)
+    close(got['select_pr_offset'], want['select_pr_offset'], atol=3e-4)
+    close(got['select_pr_scale'], want['select_pr_scale'], atol=3e-4)
     pos, scl, idx = O.det_parse(want['scores'], want['select_pr_scale'], want['select_pr_offset'])
     top2 = torch.topk(want['scores'].flatten(1), 2, 1)[0]
     print('detector top1-top2 margin (oracle):', (top2[:, 0] - top2[:, 1]).tolist())
@@ -86,6 +86,39 @@ def test_detector_maps_argmax_positions(det):
     close(res['positions'], pos, atol=2e-2)            # pixels
     close(res['scales'], scl, rtol=2e-3)
     close(res['positions'], G['det.wrap.positions'], atol=2e-2)
+
+
+def test_detector_tcgen05_correlation_480x640_32refs():
+    """BASELINE configs[1], detector half, at full size: 480x640 frame x 32 reference views.  With
+    rfn >= 16 the sliding inner product of detector.py:222-224 runs on the tcgen05 kernel (refs as the
+    K-major B operand, K = 15*15*512 split into <= 2048-term chains); its raw output per scale and
+    level, the final argmax and the decoded position are pinned to the golden run of the unmodified
+    reference (tests/golden/make_golden_det32.py)."""
+    from gen6d_b200 import ops
+    D = np.load(os.path.join(HERE, 'golden', 'det32_golden.npz'))
+    c = cases.detector_case_full()
+    net, sd = build('detector', {'name': 'det', 'network': 'detector', **c['cfg']})
+    net.load_ref_imgs(c['ref_imgs'])
+    assert all(k.w_hi is not None for k in net.ref_kernels), 'the tensor-core correlation path is not engaged'
+    que01 = ops.preprocess_u8(torch.from_numpy(c['que_imgs']).cuda(), out_c=3, imagenet_norm=False)
+    with torch.no_grad():
+        o = net._detect_nhwc(que01, return_taps=True)
+    worst = 0.0
+    for si, per_scale in enumerate(o['raw']):
+        for l, raw in enumerate(per_scale):
+            got = to_nchw(raw)
+            assert list(got.shape) == D[f'raw.s{si}.l{l}.shape'].tolist()
+            want = D[f'raw.s{si}.l{l}.sub']
+            g = sub(got)
+            worst = max(worst, float(np.abs(g - want).max() / np.abs(want).max()))
+            close(g, want, rtol=3e-5, atol=0.5)            # values ~1e5; K up to 115200 same-sign terms
+    print('raw correlation, worst relative error over 4 scales x 3 levels:', worst, 'reference argmax margin', D['margin'])
+    scores = to_nchw(o['score_predict'])
+    close(sub(scores), D['scores.sub'], atol=3e-4)
+    assert torch.argmax(scores.flatten(1), 1).tolist() == D['argmax'].tolist()          # bit-exact detection cell
+    res = net.detect_que_imgs(c['que_imgs'])
+    close(res['positions'], D['positions'], atol=2e-2)     # pixels
+    close(res['scales'], D['scales'], rtol=2e-3)
 
 
 # ------------------------------------------------------------------------------------ selector
@@ -119,15 +152,15 @@ def test_selector_scores_logits_argmax(sel):
     rfn, an = net.ref_shape
     close(scores.reshape(-1, 3, rfn, an), taps['score_vps'], rtol=1e-4, atol=1e-5)      # tap S2
     close(scores.reshape(-1, 3, rfn, an), G['sel.score_vps'], rtol=1e-4, atol=1e-5)
-    close(logits, logits_w, atol=3e-3)
-    close(angles, angles_w, atol=3e-3)
+    close(logits, logits_w, atol=3e-4)
+    close(angles, angles_w, atol=3e-4)
     top2 = torch.topk(logits_w, 2, 1)[0]
     print('selector top1-top2 margin (oracle):', (top2[:, 0] - top2[:, 1]).tolist())
     res = net.select_que_imgs(c['que_imgs'])
     idx, ang = O.sel_select(logits_w, angles_w)
     assert res['ref_idx'].tolist() == idx.tolist() == G['sel.wrap.ref_idx'].tolist()           # bit-exact viewpoint
-    close(res['angles'], ang, atol=3e-3)
-    close(res['scores'], G['sel.wrap.scores'], atol=3e-3)
+    close(res['angles'], ang, atol=3e-4)
+    close(res['scores'], G['sel.wrap.scores'], atol=3e-4)
     lg2, ang2 = net.compute_view_point_feats(que.cuda())                                      # tensor API
     close(lg2, logits, atol=1e-5)
 
@@ -151,10 +184,10 @@ def test_refiner_volume_and_pose_update():
     close(vin, want['vin'], atol=2e-4)
     close(std, want['std'], atol=2e-4)
     close(sub(mean.contiguous(), 16384), G['ref.mean.sub'], atol=2e-4)
-    close(out[:, :4], want['rotation'], atol=2e-3)
-    close(out[:, 4:6], want['offset'], atol=2e-3)
-    close(out[:, 6:7], want['scale'], atol=2e-3)
-    close(out[:, :4], G['ref.rotation'], atol=2e-3)
+    close(out[:, :4], want['rotation'], atol=3e-4)
+    close(out[:, 4:6], want['offset'], atol=3e-4)
+    close(out[:, 6:7], want['scale'], atol=3e-4)
+    close(out[:, :4], G['ref.rotation'], atol=3e-4)
     data = {'que_imgs_info': {'imgs': cases.u8_to_nchw(c['que_imgs']).cuda(), 'Ks_in': dev(c['que_Ks']),
                               'poses_in': dev(c['que_poses'])},
             'ref_imgs_info': {'imgs': cases.u8_to_nchw(c['ref_imgs']).cuda(), 'Ks': dev(c['ref_Ks']),
