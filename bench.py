@@ -38,6 +38,18 @@ WORKLOAD = ('full estimator detect->select->3x refine: synthetic 480x640 frame, 
             'selector 64 refs x 5 angles, refiner 6 views 32^3 volume, seeded random weights')
 
 
+def ncu_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the roofline kernels, from the committed
+    `ncu --set full` captures of this round (profiles/ncu_traffic.json, written by tools/ncu_summary.py)."""
+    path = os.path.join(ROOT, 'profiles', 'ncu_traffic.json')
+    if os.path.exists(path):
+        try:
+            return json.load(open(path))
+        except Exception:
+            pass
+    return {}
+
+
 def read_peaks():
     path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
     if os.path.exists(path):
@@ -93,31 +105,40 @@ def usable_cpus():
     return u()
 
 
-def cpu_pose_fn():
-    """Returns (fn, describe): fn() runs ONE network-only pose of the oracle port on the CPU."""
+def cpu_pose_fn(device='cpu'):
+    """Returns (fn, describe): fn() runs ONE network-only pose of the oracle port (a functional torch
+    restatement of the reference's three networks) on `device`: 'cpu' = the reference arm / cpu_baseline
+    on the host cores; 'cuda' = the same torch ops in eager mode on the B200 (cuDNN / cuBLAS fp32, TF32
+    disabled) -- the same-box GPU comparison point BASELINE.md 4.6 asks for."""
     from gen6d_b200 import geometry as G
     from gen6d_b200 import synthetic as syn
     from oracle import gen6d_oracle as O
     torch.set_num_threads(min(usable_cpus(), 64))
-    sds = syn.seeded_state_dicts()
+    if device != 'cpu':
+        torch.backends.cudnn.allow_tf32 = False
+        torch.backends.cuda.matmul.allow_tf32 = False
+    dv = lambda t: t.to(device)
+    sds = {k: {n: dv(v) for n, v in sd.items()} for k, sd in syn.seeded_state_dicts().items()}
     db = syn.synthetic_database()
     g = torch.Generator().manual_seed(5)
     to01 = lambda u8: torch.from_numpy(u8.astype(np.float32) / 255)
-    det_refs = torch.rand(32, 3, 128, 128, generator=g)
-    sel_refs = torch.rand(5, 64, 3, 128, 128, generator=g)
+    det_refs = dv(torch.rand(32, 3, 128, 128, generator=g))
+    sel_refs = dv(torch.rand(5, 64, 3, 128, 128, generator=g))
     ids = db.get_img_ids()[:64]
-    poses = torch.from_numpy(np.stack([db.get_pose(i) for i in ids]))
+    poses = dv(torch.from_numpy(np.stack([db.get_pose(i) for i in ids])))
     t0 = time.perf_counter()
     with torch.no_grad():
         det_feats = O.det_load_refs(sds['detector'], det_refs)
-        sel_feats, embed = O.sel_load_refs(sds['selector'], sel_refs, poses, torch.zeros(3), torch.tensor([0., 0., 1.]))
+        sel_feats, embed = O.sel_load_refs(sds['selector'], sel_refs, poses, dv(torch.zeros(3)), dv(torch.tensor([0., 0., 1.])))
+    if device != 'cpu':
+        torch.cuda.synchronize()
     load_s = time.perf_counter() - t0
-    frame = to01(db.get_image('11')).permute(2, 0, 1)[None].contiguous()
-    crop = torch.rand(1, 3, 128, 128, generator=g)
-    rq, rr = torch.rand(1, 3, 128, 128, generator=g), torch.rand(1, 6, 3, 128, 128, generator=g)
-    K = torch.tensor([[[304., 0, 64], [0, 304., 64], [0, 0, 1]]])
-    qp = torch.from_numpy(db.get_pose('11'))[None]
-    rp = torch.from_numpy(np.stack([db.get_pose(i) for i in ids[:6]]))[None]
+    frame = dv(to01(db.get_image('11')).permute(2, 0, 1)[None].contiguous())
+    crop = dv(torch.rand(1, 3, 128, 128, generator=g))
+    rq, rr = dv(torch.rand(1, 3, 128, 128, generator=g)), dv(torch.rand(1, 6, 3, 128, 128, generator=g))
+    K = dv(torch.tensor([[[304., 0, 64], [0, 304., 64], [0, 0, 1]]]))
+    qp = dv(torch.from_numpy(db.get_pose('11'))[None])
+    rp = dv(torch.from_numpy(np.stack([db.get_pose(i) for i in ids[:6]]))[None])
     det_cfg = {'vgg_score_stats': syn.DET_SCORE_STATS}
 
     def one_pose():
@@ -130,6 +151,134 @@ def cpu_pose_fn():
                 O.ref_forward(sds['refiner'], rq, K, qp, rr, K[:, None].repeat(1, 6, 1, 1), rp, 32)
 
     return one_pose, {'reference_set_load_s': round(load_s, 2)}
+
+
+def torch_cuda_baseline(steps=10, warm=3):
+    """PyTorch eager (cuDNN/cuBLAS fp32, allow_tf32 = False) on the same B200: the oracle port on CUDA
+    tensors, device-resident inputs, CUDA events.  A reported comparison point, not a target."""
+    fn, info = cpu_pose_fn('cuda')
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    return {'value': 1e3 / ms, 'unit': 'poses/s', 'ms_per_step': ms, 'steps': steps,
+            'what': f'oracle port (functional torch {torch.__version__} restatement of the reference networks) in eager mode on '
+                    'cuda:0, cudnn.allow_tf32 = matmul.allow_tf32 = False, one frame at a time, inputs resident, network-only pose'}
+
+
+def run_torch_cuda_arm(args, rank, world):
+    if rank != 0:
+        return
+    torch.cuda.set_device(0)
+    r = torch_cuda_baseline(args.steps, args.warmup)
+    print(json.dumps({'impl': 'torch-cuda', 'metric': METRIC, 'value': r['value'], 'unit': 'poses/s', 'n_gpus': 1,
+                      'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': r['ms_per_step'], 'higher_is_better': True,
+                      'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+                      'config': {'workload': WORKLOAD, 'path': r['what']}}))
+
+
+def add_accuracy(est, db):
+    """north_star: "at matched ADD-0.1d on synthetic inputs".  The 20 frames of tests/golden/add_golden.npz
+    through predict(); ADD-0.1d / Prj-5 against the database's ground truth on the device (g6d_pose_errors),
+    next to the values the unmodified reference estimator scored on the same frames (seeded random weights:
+    both rates are what an untrained network gives; the check is that they MATCH, frame by frame)."""
+    path = os.path.join(ROOT, 'tests', 'golden', 'add_golden.npz')
+    if not os.path.exists(path):
+        return None
+    from gen6d_b200 import metrics as M
+    A = np.load(path)
+    ids = [str(int(i)) for i in A['frame_ids']]
+    poses = np.stack([est.predict(db.get_image(f), db.get_K(f))[0] for f in ids], 0)
+    pts, diameter = db.object_point_cloud.astype(np.float32), float(A['diameter'])
+    err = M.pose_errors(pts, poses, A['poses_gt'], A['Ks']).cpu().numpy().astype(np.float64)
+    return {'frames': len(ids), 'add_0.1d': float(np.mean(err[:, 1] < 0.1 * diameter)), 'prj_5': float(np.mean(err[:, 0] < 5)),
+            'reference_add_0.1d': float(A['res.add-0.1d']), 'reference_prj_5': float(A['res.prj-5']),
+            'max_abs_add_error_diff_over_0.1d': float(np.abs(err[:, 1] - A['obj_err']).max() / (0.1 * diameter)),
+            'max_rel_prj_error_diff': float((np.abs(err[:, 0] - A['prj_err']) / A['prj_err']).max()),
+            'reference': 'unmodified reference estimator on CPU, scored by its utils/pose_utils.py (tests/golden/make_golden_add.py)'}
+
+
+def sharded_section(world, rank):
+    """BASELINE configs[3] / [4] on the driver's clock (world > 1): selector with the reference views sharded
+    (64 refs x 36 rotation bins per GPU = 2304 slices, 1.585 GB stack per GPU; exact cross-GPU InstanceNorm
+    statistics) and refiner with the pose batch sharded (32 poses per GPU, 6 views, 32^3).  CUDA events,
+    max over ranks; weak-scaling efficiency = the same per-GPU work run unsharded on this rank / sharded."""
+    import torch.distributed as dist
+    sys.path.insert(0, os.path.join(ROOT, 'tests'))
+    from golden import cases
+    from gen6d_b200 import dist as gdist, ops
+    from gen6d_b200.network import name2network
+    from gen6d_b200.weights import seeded_state_dict
+    comm = gdist.Comm()
+
+    def build(name, cfg):
+        net = name2network[name](cfg)
+        net.load_state_dict(seeded_state_dict(net, 0))
+        return net.cuda().eval()
+
+    def timed(fn, iters, warm=2):
+        for _ in range(warm):
+            fn()
+        dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(iters):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        t = torch.tensor([e0.elapsed_time(e1) / iters], device='cuda', dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t[0])
+
+    per_gpu_refs, bins, per_gpu_poses = 64, 36, 32
+    out = {}
+    # ---- selector: references sharded; every rank synthesises the same full set and keeps its slice
+    g = torch.Generator().manual_seed(1)
+    refs = per_gpu_refs * world
+    poses = cases.sphere_poses(3, refs)
+    blocks = (torch.rand(bins, refs, 8, 8, 3, generator=g) * 255).to(torch.uint8).numpy()
+    imgs = np.kron(blocks, np.ones((1, 1, 16, 16, 1), np.uint8))
+    que = cases.rand_images_u8(5, 1, 128, 128, 3)
+    center, vert = np.zeros(3, np.float32), np.array([0, 0, 1], np.float32)
+    r0, r1 = comm.shard_range(refs)
+    local = build('selector', {'selector_angle_num': bins})
+    local.load_ref_imgs(np.ascontiguousarray(imgs[:, r0:r1]), poses[r0:r1], center, vert)
+    t_local = timed(lambda: local.select_que_imgs(que), 5)
+    del local
+    torch.cuda.empty_cache()
+    sel = gdist.shard_selector(build('selector', {'selector_angle_num': bins}), comm)
+    sel.load_ref_imgs(imgs, poses, center, vert)
+    t_shard = timed(lambda: sel.select_que_imgs(que), 5)
+    out['selector_ref_shard'] = {
+        'workload': f'{refs} refs x {bins} bins over {world} GPUs ({per_gpu_refs} refs = {per_gpu_refs * bins} slices = '
+                    f'{per_gpu_refs * bins * 688128 / 1e9:.3f} GB of reference stack per GPU), 1 query 128x128',
+        'ms_per_query': t_shard, 'queries_per_s': 1e3 / t_shard, 'ms_per_query_same_shard_unsharded_1gpu': t_local,
+        'weak_scaling_efficiency': t_local / t_shard,
+        'collectives': sel.comm_stats() if hasattr(sel, 'comm_stats') else None}
+    del sel
+    torch.cuda.empty_cache()
+    # ---- refiner: pose batch sharded
+    rfr = build('refiner', {})
+    rc = cases.refiner_case(seed=7, qn=per_gpu_poses)        # every rank refines its own 32 poses (same synthetic set)
+    dev = lambda x: torch.from_numpy(x).cuda()
+    a = [ops.preprocess_u8(dev(rc['que_imgs']), 4, True), dev(rc['que_Ks']), dev(rc['que_poses']),
+         ops.preprocess_u8(dev(rc['ref_imgs']), 4, True), dev(rc['ref_Ks']), dev(rc['ref_poses'])]
+    with torch.no_grad():
+        t_one = timed(lambda: rfr._forward_nhwc(*a), 3, warm=1)
+        t_all = timed(lambda: comm.all_gather_cat(rfr._forward_nhwc(*a), dim=0), 3, warm=1)
+    out['refiner_pose_shard'] = {
+        'workload': f'{per_gpu_poses * world} poses over {world} GPUs ({per_gpu_poses} per GPU), 6 views, 32^3 volume, one iteration '
+                    '(configs[4] runs 6 of them)',
+        'ms_per_iteration': t_all, 'pose_iterations_per_s': per_gpu_poses * world / t_all * 1e3,
+        'ms_per_iteration_unsharded_1gpu': t_one, 'weak_scaling_efficiency': t_one / t_all}
+    return out
 
 
 def run_reference_arm(args, rank, world):
@@ -313,17 +462,24 @@ def run_ours(args, rank, world, local_rank):
     peaks = read_peaks()
     conv = stats.get('g6d_conv_tc', {'ms': 0, 'work': 0, 'n': 1})
     ffma = stats.get('g6d_conv', {'ms': 0, 'work': 0, 'n': 0})
-    roof = {'kernel': 'conv_tc_kernel (tcgen05 implicit-GEMM convolution, 3xTF32 fp32-faithful mode)', 'bound': 'tensor',
-            'achieved': conv['work'] / max(conv['ms'], 1e-9) / 1e9, 'peak': peaks['bf16_tflops'], 'unit': 'TFLOP/s',
-            'traffic': None,
-            'peak_source': f"{peaks['src']} bf16 dense GEMM (sustained); achieved counts fp32-equivalent flops 2MNK, each "
-                           "issued as 3 TF32 MMAs, so 1/6 of this peak is the ceiling of the parity mode",
+    f16 = ops.conv_kind() == _lib.TC_F16
+    split = 3.0 if f16 else 6.0             # bf16-peak units per fp32-equivalent flop: 3 fp16 MMAs, or 3 TF32 MMAs at half rate
+    traffic = ncu_traffic()
+    roof = {'kernel': 'conv_tc2_kernel / conv_tcflat_kernel (tcgen05 implicit-GEMM convolution, fp32-faithful 3-term operand split, '
+                      + ('fp16 hi + 2^11-scaled fp16 lo halves, kind::f16' if f16 else 'tf32 hi/lo halves, kind::tf32') + ')',
+            'bound': 'tensor', 'achieved': conv['work'] / max(conv['ms'], 1e-9) / 1e9, 'peak': peaks['bf16_tflops'], 'unit': 'TFLOP/s',
+            'traffic': traffic.get('conv'),
+            'peak_source': f"{peaks['src']} bf16 dense GEMM (sustained); achieved counts fp32-equivalent flops 2MNK, each issued as 3 "
+                           + ('fp16' if f16 else 'TF32') + f" MMAs, so 1/{split:g} of this peak is the ceiling of the parity mode",
             'launches_per_step': conv['n'] // 2, 'ms_per_step': conv['ms'] / 2,
             'share_of_step': conv['ms'] / max(eager_ms, 1e-9),
+            'timing': 'CUDA events around every launch in an extra serialised pass (branch streams off, one frame): ms_per_step here '
+                      'is un-overlapped kernel time and exceeds the top-level ms_per_step, which overlaps frames and branches',
             'ffma_fallback': {'launches_per_step': ffma['n'] // 2, 'ms_per_step': ffma['ms'] / 2,
                               'tflops': ffma['work'] / max(ffma['ms'], 1e-9) / 1e9}}
     roof['frac'] = roof['achieved'] / roof['peak']
-    roof['frac_of_3xtf32_ceiling'] = roof['achieved'] / (roof['peak'] / 6.0)
+    roof['frac_of_split_ceiling'] = roof['achieved'] / (roof['peak'] / split)
+    roof['frac_of_3xtf32_ceiling'] = roof['achieved'] / (roof['peak'] / 6.0)     # round-1 yardstick, kept for continuity
     extra = []
     for key, label in (('g6d_sel_corr_score3', 'selector correlation + rotated-similarity score, 3 levels (S2)'),
                        ('g6d_ref_volume_fill', 'refiner unproject-and-aggregate volume fill (R2)')):
@@ -331,8 +487,12 @@ def run_ours(args, rank, world, local_rank):
             s = stats[key]
             ach = s['work'] / max(s['ms'], 1e-9) / 1e6
             extra.append({'kernel': label, 'bound': 'hbm', 'achieved': ach, 'peak': peaks['hbm_gbs'], 'unit': 'GB/s',
-                          'frac': ach / peaks['hbm_gbs'], 'us_per_launch': s['ms'] / s['n'] * 1e3, 'traffic': None})
+                          'frac': ach / peaks['hbm_gbs'], 'us_per_launch': s['ms'] / s['n'] * 1e3,
+                          'algorithmic_bytes_per_launch': s['work'] / s['n'],
+                          'traffic': traffic.get('s2' if 'score3' in key else 'r2')})
 
+    accuracy = add_accuracy(est, db) if rank == 0 else None
+    sharded = sharded_section(world, rank) if world > 1 else None
     if rank != 0:
         return
     value = world * args.steps / (dev_ms * 1e-3)
@@ -351,7 +511,15 @@ def run_ours(args, rank, world, local_rank):
                     'single_frame_latency': {'value': e2e_v, 'unit': 'poses/s', 'ms_per_step': e2e_wall_ms / args.steps,
                                              'api': 'Gen6DEstimator.predict(numpy frame, K), one frame at a time'}},
             'gpu_launches': int(launches), 'roofline': roof, 'kernels': extra, 'clocks': clocks}
+    if accuracy is not None:
+        line['accuracy'] = accuracy
+    if sharded is not None:
+        line['sharded'] = sharded
     if world == 1:
+        try:
+            line['torch_cuda_baseline'] = torch_cuda_baseline(5, 2)
+        except Exception as e:  # noqa: BLE001  (a reported comparison point must not take the bench line down)
+            line['torch_cuda_baseline'] = {'unavailable': repr(e)[:200]}
         fn, info = cpu_pose_fn()        # sets torch threads to the usable-CPU count for the CPU baseline
         fn()
         n = 2
@@ -370,7 +538,7 @@ def main():
     ap.add_argument('--gpus', type=int, default=1)
     ap.add_argument('--steps', type=int, default=None)
     ap.add_argument('--warmup', type=int, default=None)
-    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference', 'torch-cuda'])
     args = ap.parse_args()
     rank, world = int(os.environ.get('RANK', 0)), int(os.environ.get('WORLD_SIZE', 1))
     local_rank = int(os.environ.get('LOCAL_RANK', 0))
@@ -378,6 +546,11 @@ def main():
         args.steps = 5 if args.steps is None else args.steps
         args.warmup = 1 if args.warmup is None else args.warmup
         run_reference_arm(args, rank, world)
+        return
+    if args.impl == 'torch-cuda':
+        args.steps = 10 if args.steps is None else args.steps
+        args.warmup = 3 if args.warmup is None else max(3, args.warmup)
+        run_torch_cuda_arm(args, rank, world)
         return
     args.steps = 20 if args.steps is None else args.steps
     args.warmup = 3 if args.warmup is None else max(3, args.warmup)

@@ -597,8 +597,9 @@ static int fill_tc_params(const g6d_conv_desc* d, int kind, ConvTcP& p) {
     // K chains of same-sign products (detector correlation: K = 115200 of post-ReLU features)
     // that is a systematic bias of ~4e-5 relative.  For long-K problems (K > 8192) the chain per
     // CTA is bounded to 2048 terms and the partials are summed in fp32 round-to-nearest.
-    const int max_kb = TC_MAX_K_PER_CHAIN / bk;
-    const int min_splits = K > 8192 ? (p.kblocks + max_kb - 1) / max_kb : 1;
+    const int chain = d->max_chain_k > 0 ? d->max_chain_k : (K > 8192 ? TC_MAX_K_PER_CHAIN : 0);
+    const int max_kb = chain > bk ? chain / bk : 1;
+    const int min_splits = chain > 0 ? (p.kblocks + max_kb - 1) / max_kb : 1;
     splits = splits < min_splits ? min_splits : splits;
     splits = splits > 64 ? 64 : splits;
     p.kb_per_split = (p.kblocks + splits - 1) / splits;
@@ -1013,7 +1014,8 @@ static int fill_flat_params(const g6d_conv_desc* d, int kind, ConvFlatP& p, int*
     const long long K = (long long)d->Cin * d->kd * d->kh * d->kw;
     int splits = 1;
     if (ctas < kNumSMs && p.cblocks >= 2) splits = (int)((kNumSMs + ctas - 1) / ctas);
-    if (K > 8192) { const int ms = (int)((K + TC_MAX_K_PER_CHAIN - 1) / TC_MAX_K_PER_CHAIN); splits = splits < ms ? ms : splits; }
+    const long long chain = d->max_chain_k > 0 ? d->max_chain_k : (K > 8192 ? TC_MAX_K_PER_CHAIN : 0);
+    if (chain > 0) { const int ms = (int)((K + chain - 1) / chain); splits = splits < ms ? ms : splits; }
     splits = splits > p.cblocks ? p.cblocks : splits;
     splits = splits < 1 ? 1 : splits;
     p.cb_per_split = (p.cblocks + splits - 1) / splits;

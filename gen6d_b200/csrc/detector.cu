@@ -145,9 +145,44 @@ __global__ void det_parse_kernel(const float* __restrict__ scores, const float* 
     }
 }
 
+// Second half of the row-decomposed sliding inner product (detector.py:222-224 F.conv2d(que, ref) with
+// the reference features as k x k kernels):  out[y,x,r] = sum_ky partial[y + ky, x, ky*rfn + r], where
+// partial = (1 x k convolution with k*rfn output channels (ky-major), zero padding k/2 in BOTH axes) holds,
+// for every input row y' = y + ky - k/2, the contribution of kernel row ky.  The 1 x k form turns the
+// N = rfn (32) GEMM of the direct formulation into an N = k*rfn (480) one: full-width tensor-core tiles.
+__global__ void det_corr_rowsum_kernel(const float4* __restrict__ partial, float4* __restrict__ out, long long total,
+                                       int H, int W, int k, int rfn4) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const int r = (int)(i % rfn4);
+    long long t = i / rfn4;
+    const int x = (int)(t % W); t /= W;
+    const int y = (int)(t % H);
+    const long long q = t / H;
+    const long long row_stride = (long long)W * k * rfn4;            // float4 per partial row y'
+    const float4* p = partial + (q * (H + k - 1) + y) * row_stride + (long long)x * k * rfn4 + r;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int ky = 0; ky < k; ++ky) {
+        const float4 v = __ldg(p + ky * row_stride + ky * rfn4);
+        acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    }
+    out[i] = acc;
+}
+
 }  // namespace g6d
 
 using namespace g6d;
+
+extern "C" int g6d_det_corr_rowsum(const float* partial, float* out, int qn, int H, int W, int k, int rfn,
+                                   g6d_stream_t stream) {
+    G6D_REQUIRE(partial && out && qn > 0 && H > 0 && W > 0 && k > 0 && rfn > 0 && (rfn & 3) == 0,
+                "g6d_det_corr_rowsum: bad args (rfn must be a multiple of 4)");
+    const long long total = (long long)qn * H * W * (rfn / 4);
+    det_corr_rowsum_kernel<<<ceil_div(total, 256), 256, 0, as_stream(stream)>>>(
+        reinterpret_cast<const float4*>(partial), reinterpret_cast<float4*>(out), total, H, W, k, rfn / 4);
+    G6D_CHECK_LAUNCH("g6d_det_corr_rowsum");
+    return G6D_OK;
+}
 
 extern "C" int g6d_det_score_fuse(const g6d_det_maps* host_maps, int qn, const float* w1, const float* b1,
                                   const float* w2, const float* b2, float* out, g6d_stream_t stream) {

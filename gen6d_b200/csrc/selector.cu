@@ -1,5 +1,7 @@
 // Selector-specific kernels: the HBM-bound correlation + rotated-similarity score (S2), the
 // closed-form first-InstanceNorm statistics, and the small latency-bound tail ops (S4).
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace g6d {
@@ -90,28 +92,39 @@ __device__ __forceinline__ float row_dot(const float4* __restrict__ rp, const fl
     return t;
 }
 
-template <int C>
-__global__ void __launch_bounds__(256) sel_corr_dots_kernel(const ScoreLevels L, float* __restrict__ t_out) {
+// FUSED: the warp that completes the last row pair of a (level, slice) item -- found with one
+// atomic counter per item -- also reduces that item's P inner products to the score, with the
+// reference's operation order (selector.py:192-194: s / max first, then sum of s * (s / max); IEEE
+// behaviour for max <= 0, no epsilon).  No second launch, no second pass over t from another kernel.
+template <int C, bool FUSED>
+__global__ void __launch_bounds__(256) sel_corr_dots_kernel(const ScoreLevels L, float* __restrict__ t_out,
+                                                            int* __restrict__ done, float* __restrict__ score) {
     const int lane = threadIdx.x & 31;
     const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
     const long long rows = L.row_end[2];
-    auto locate = [&](long long row, const float4*& rp, const float4*& qp) {
+    auto locate = [&](long long row, const float4*& rp, const float4*& qp, int& item, int& P, long long& first) {
         // static selects (no dynamic indexing of the parameter struct -> no local-memory copy)
         const bool l0 = row < L.row_end[0], l1 = row < L.row_end[1];
-        const long long local = row - (l0 ? 0 : (l1 ? L.row_end[0] : L.row_end[1]));      // = s*P_l + p
-        const int P = l0 ? L.P[0] : (l1 ? L.P[1] : L.P[2]);
+        const long long lbase = l0 ? 0 : (l1 ? L.row_end[0] : L.row_end[1]);
+        const long long local = row - lbase;                                                // = s*P_l + p
+        P = l0 ? L.P[0] : (l1 ? L.P[1] : L.P[2]);
         const float* ref = l0 ? L.ref[0] : (l1 ? L.ref[1] : L.ref[2]);
         const float* q = l0 ? L.q[0] : (l1 ? L.q[1] : L.q[2]);
-        const int p = (int)(local % P);
+        const int sl = (int)(local / P);
+        const int p = (int)(local - (long long)sl * P);
+        item = (l0 ? 0 : (l1 ? 1 : 2)) * L.S + sl;
+        first = lbase + (long long)sl * P;
         rp = reinterpret_cast<const float4*>(ref + local * C);
         qp = reinterpret_cast<const float4*>(q + (long long)p * C);
     };
     for (long long row = warp * 2; row < rows; row += nwarps * 2) {
         const float4 *r0, *q0, *r1, *q1;
-        locate(row, r0, q0);
+        int item0, item1, P0, P1;
+        long long first0, first1;
+        locate(row, r0, q0, item0, P0, first0);
         const bool two = row + 1 < rows;
-        locate(two ? row + 1 : row, r1, q1);
+        locate(two ? row + 1 : row, r1, q1, item1, P1, first1);
         float t0 = row_dot<C>(r0, q0, lane);
         float t1 = row_dot<C>(r1, q1, lane);
         t0 = warp_sum(t0);
@@ -120,10 +133,40 @@ __global__ void __launch_bounds__(256) sel_corr_dots_kernel(const ScoreLevels L,
             t_out[row] = t0;
             if (two) t_out[row + 1] = t1;
         }
+        if (FUSED) {
+            // publish, count, and let the last arriver of each item finish it (a pair straddles two
+            // items only when P is odd; handled by counting the two rows separately)
+            int last0 = 0, last1 = 0;
+            if (lane == 0) {
+                __threadfence();
+                if (two && item1 == item0) {
+                    last0 = atomicAdd(done + item0, 2) + 2 == P0;
+                } else {
+                    last0 = atomicAdd(done + item0, 1) + 1 == P0;
+                    if (two) last1 = atomicAdd(done + item1, 1) + 1 == P1;
+                }
+            }
+            last0 = __shfl_sync(0xffffffffu, last0, 0);
+            last1 = __shfl_sync(0xffffffffu, last1, 0);
+#pragma unroll 1
+            for (int h = 0; h < 2; ++h) {
+                if (!(h == 0 ? last0 : last1)) continue;                 // warp-uniform
+                const int item = h == 0 ? item0 : item1, P = h == 0 ? P0 : P1;
+                const float* tp = t_out + (h == 0 ? first0 : first1);
+                __threadfence();                                         // acquire: the other warps' t values
+                float m = -INFINITY;
+                for (int p = lane; p < P; p += 32) m = fmaxf(m, __ldcg(tp + p));
+                m = warp_max(m);
+                float acc = 0.f;
+                for (int p = lane; p < P; p += 32) { const float v = __ldcg(tp + p); acc += v * (v / m); }
+                acc = warp_sum(acc);
+                if (lane == 0) score[item] = acc;       // [3, S]
+            }
+        }
     }
 }
 
-// one warp per (level, slice): score = sum_p t*(t/max_p t), reference operation order
+// one warp per (level, slice): score = sum_p t*(t/max_p t), reference operation order (unfused path)
 __global__ void sel_corr_finish_kernel(const ScoreLevels L, const float* __restrict__ t, float* __restrict__ score) {
     const int lane = threadIdx.x & 31;
     const int item = (int)(((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
@@ -313,6 +356,12 @@ extern "C" int g6d_sel_corr_score(const float* ref, const float* q, int S, int P
     return G6D_OK;
 }
 
+extern "C" long long g6d_sel_corr_score3_workspace_bytes(int S, int P0, int P1, int P2) {
+    if (S <= 0 || P0 <= 0 || P1 <= 0 || P2 <= 0) { set_error("g6d_sel_corr_score3_workspace_bytes: bad args"); return -1; }
+    const long long rows = (long long)S * ((long long)P0 + P1 + P2);
+    return ((rows + 3) / 4) * 4 * (long long)sizeof(float) + 3ll * S * (long long)sizeof(int);
+}
+
 extern "C" int g6d_sel_corr_score3(const float* ref0, const float* ref1, const float* ref2, const float* q0,
                                    const float* q1, const float* q2, int S, int P0, int P1, int P2, int C, float* score,
                                    float* ws, g6d_stream_t stream) {
@@ -329,7 +378,18 @@ extern "C" int g6d_sel_corr_score3(const float* ref0, const float* ref1, const f
     long long grid = (pairs + 7) / 8;                    // 8 warps per CTA, one row pair per warp per trip
     const long long full = 8ll * kNumSMs;                // 8 CTAs x 256 threads = 64 warps per SM
     if (grid > full) grid = full;
-    sel_corr_dots_kernel<512><<<(unsigned)grid, 256, 0, st>>>(L, ws);
+    // workspace: [rows] floats of per-location inner products, then 3*S completion counters
+    int* done = reinterpret_cast<int*>(ws + ((L.row_end[2] + 3) / 4) * 4);
+    static int fused = -1;
+    if (fused < 0) { const char* e = getenv("G6D_S2_FUSED"); fused = (e && e[0] == '0') ? 0 : 1; }
+    if (fused) {
+        cudaError_t e = cudaMemsetAsync(done, 0, sizeof(int) * 3 * S, st);
+        if (e != cudaSuccess) { set_error("g6d_sel_corr_score3: memset: %s", cudaGetErrorString(e)); return G6D_ECUDA; }
+        sel_corr_dots_kernel<512, true><<<(unsigned)grid, 256, 0, st>>>(L, ws, done, score);
+        G6D_CHECK_LAUNCH("g6d_sel_corr_score3");
+        return G6D_OK;
+    }
+    sel_corr_dots_kernel<512, false><<<(unsigned)grid, 256, 0, st>>>(L, ws, nullptr, nullptr);
     G6D_CHECK_LAUNCH("g6d_sel_corr_score3(dots)");
     sel_corr_finish_kernel<<<ceil_div(3ll * S * 32, 256), 256, 0, st>>>(L, ws, score);
     G6D_CHECK_LAUNCH("g6d_sel_corr_score3(finish)");

@@ -126,6 +126,35 @@ class Gen6DEstimator:
         return pose, inter
 
 
+    def predict_batch(self, que_imgs, que_Ks, pose_inits=None):
+        """predict() for a batch of independent frames of one size (row f3): qn frames go through ONE
+        detect stage, ONE select stage and ONE refine stage per iteration -- 2 + refine_iter graph launches
+        and device->host reads for the whole batch instead of per frame -- with the small per-frame camera
+        algebra on the host in between.  Same results as predict() frame by frame.
+        que_imgs: list / array of uint8 [h,w,3]; que_Ks: [qn,3,3].  Returns (poses [qn,3,4], inter dict of lists)."""
+        qn, res = len(que_imgs), self.cfg['ref_resolution']
+        que_Ks = [np.asarray(K) for K in que_Ks]
+        frames = self.detector.upload_frame(np.stack(que_imgs, 0))            # [qn,h,w,3] once, for all stages
+        inter = {}
+        if pose_inits is None:
+            det = self.detector.detect_que_imgs(None, que_dev=frames)
+            Ms = [G.crop_similarity(None, det['positions'][i], 1 / det['scales'][i], 0, res)[1] for i in range(qn)]
+            sel = self.selector.select_from_frames(frames, Ms, res)
+            inter.update(det_position=det['positions'], det_scale_r2q=det['scales'], det_que_img=sel['que_imgs'],
+                         sel_angle_r2q=sel['angles'], sel_scores=sel['scores'], sel_ref_idx=sel['ref_idx'])
+            poses = np.stack([G.pose_from_similarity(det['positions'][i], det['scales'][i], sel['angles'][i],
+                                                     self.ref_info['poses'][sel['ref_idx'][i]], self.ref_info['Ks'][sel['ref_idx'][i]],
+                                                     que_Ks[i], self.ref_info['center']) for i in range(qn)], 0)
+        else:
+            poses = np.stack(pose_inits, 0)
+        if self.refiner is not None:
+            chain = [poses]
+            for _ in range(self.cfg['refine_iter']):
+                poses = self.refiner.refine_batch(frames, que_Ks, poses, size=128, ref_num=6, ref_even=True)
+                chain.append(poses)
+            inter['refine_poses'] = chain
+        return poses, inter
+
     # ------------------------------------------------------------------ throughput API
     def worker_clone(self):
         import copy
@@ -143,13 +172,14 @@ class Gen6DEstimator:
         pool = getattr(self, '_pool', None)
         if pool is not None:
             pool.shutdown(wait=True)
-        self._workers, self._pool, self._workers_gen = None, None, None
+        self._workers, self._pool, self._workers_gen, self._warm = None, None, None, set()
 
-    def predict_many(self, que_imgs, que_Ks, workers=2):
-        """Poses for independent frames, `workers` frames in flight: each worker thread owns a clone
-        of the networks (shared weights / reference features, private CUDA graphs) and a CUDA
-        stream, so one frame's host geometry (OpenCV warps, view selection) overlaps another frame's
-        kernels.  Same per-frame computation and results as predict(); returns [(pose, inter)]."""
+    def predict_many(self, que_imgs, que_Ks, workers=2, batch=1):
+        """Poses for independent frames: `workers` host threads, each with a clone of the networks (shared
+        weights / reference features, private CUDA graphs) and a CUDA stream, each pushing `batch` frames
+        at a time through predict_batch (batch = 1: plain predict), so one batch's host geometry overlaps
+        another batch's kernels.  Same results as predict(); returns [(pose, inter)] (inter of a batched
+        frame holds that frame's slices)."""
         from concurrent.futures import ThreadPoolExecutor
         # The clones share weights / reference features by reference and own captured graphs over them:
         # rebuild them whenever any module's state changed (build() on another object, load_state_dict).
@@ -158,20 +188,37 @@ class Gen6DEstimator:
             self._workers = [(self.worker_clone(), torch.cuda.Stream()) for _ in range(workers)]
             self._workers_gen = self._generation()
             self._pool = ThreadPoolExecutor(workers)
-            for est, stream in self._workers:        # capture every worker's stage graphs one at a time
+            self._warm = set()
+        n = len(que_imgs)
+        batch = max(1, min(batch, n))
+        if batch not in self._warm:                  # capture every worker's stage graphs for this batch size, one at a time
+            for est, stream in self._workers:
                 stream.wait_stream(torch.cuda.current_stream())
                 with torch.cuda.stream(stream):
-                    est.predict(que_imgs[0], que_Ks[0])
+                    if batch == 1:
+                        est.predict(que_imgs[0], que_Ks[0])
+                    else:
+                        est.predict_batch([que_imgs[i % n] for i in range(batch)], [que_Ks[i % n] for i in range(batch)])
                     stream.synchronize()
-        results = [None] * len(que_imgs)
+            self._warm.add(batch)
+        results = [None] * n
         caller = torch.cuda.current_stream()
+        chunks = [list(range(b, min(b + batch, n))) for b in range(0, n, batch)]
 
         def run(w):
             est, stream = self._workers[w]
             stream.wait_stream(caller)               # order after whatever the caller enqueued (uploads, a rebuild)
             with torch.cuda.stream(stream):
-                for i in range(w, len(que_imgs), workers):
-                    results[i] = est.predict(que_imgs[i], que_Ks[i])
+                for c in range(w, len(chunks), workers):
+                    idx = chunks[c]
+                    if batch == 1:
+                        results[idx[0]] = est.predict(que_imgs[idx[0]], que_Ks[idx[0]])
+                        continue
+                    pad = idx + [idx[-1]] * (batch - len(idx))        # a short last chunk reuses the captured batch size
+                    poses, inter = est.predict_batch([que_imgs[i] for i in pad], [que_Ks[i] for i in pad])
+                    for j, i in enumerate(idx):
+                        one = {k: ([p[j] for p in v] if k == 'refine_poses' else v[j]) for k, v in inter.items()}
+                        results[i] = (poses[j], one)
                 stream.synchronize()
 
         list(self._pool.map(run, range(workers)))

@@ -56,10 +56,23 @@ class Detector(PackedModule):
         kernels = []
         for f in feats:
             rfn, k, _, c = f.shape
-            flat = f.reshape(rfn, k * k * c)
-            pc = ops.PackedConv(ops.transpose_to_packed(flat), None, c, rfn, (1, k, k), 1, (0, k // 2, k // 2))
-            if rfn >= 16:   # channels-last features [rfn, (ky,kx,c)] are already the K-major B operand
-                pc.w_hi, pc.w_lo, pc.kind = ops.split_operand(flat, ops.tc_kind_for(c))
+            kind = ops.tc_kind_for(c)
+            if rfn >= 16 and rfn % 4 == 0 and kind is not None and ops.conv_path() == 'tc' and self.cfg.get('corr_rows', True):
+                # Tensor-core path, row-decomposed: the k x k kernels become a 1 x k convolution with
+                # k*rfn output channels (channel = ky*rfn + r) whose per-row results g6d_det_corr_rowsum
+                # adds up.  N = k*rfn (480 at 15 x 15 x 32 refs) fills full 128-wide MMA tiles; the direct
+                # form's N = rfn = 32 pays 40 cycles per MMA against a 16-cycle tensor floor.
+                flat = f.permute(1, 0, 2, 3).reshape(k * rfn, k * c).contiguous()      # [(ky, r), (kx, c)], K-major B operand
+                pc = ops.PackedConv(None, None, c, k * rfn, (1, 1, k), 1, (0, k // 2, k // 2))
+                pc.w_hi, pc.w_lo, pc.kind = ops.split_operand(flat, kind)
+                pc.rows = (k, rfn)
+                pc.max_chain_k = 2048        # post-ReLU features x post-ReLU features: same-sign products
+            else:
+                flat = f.reshape(rfn, k * k * c)
+                pc = ops.PackedConv(ops.transpose_to_packed(flat), None, c, rfn, (1, k, k), 1, (0, k // 2, k // 2))
+                if rfn >= 16 and kind is not None:   # channels-last features [rfn, (ky,kx,c)] are already the K-major B operand
+                    pc.w_hi, pc.w_lo, pc.kind = ops.split_operand(flat, kind)
+                    pc.max_chain_k = 2048
             kernels.append(pc)
         self.ref_kernels = kernels
         self.bump_generation()          # captured graphs / worker clones hold pointers to the previous reference set
@@ -79,7 +92,12 @@ class Detector(PackedModule):
     def _raw_correlation(self, que01):
         """The three sliding inner products of detector.py:222-224 for one scale."""
         feats = self._features(que01)
-        return [ops.conv(f, k) for f, k in zip(feats, self.ref_kernels)]
+        out = []
+        for f, pc in zip(feats, self.ref_kernels):
+            y = ops.conv(f, pc)
+            rows = getattr(pc, 'rows', None)
+            out.append(ops.det_corr_rowsum(y, *rows) if rows is not None else y)
+        return out
 
     def _detect_nhwc(self, que01, return_taps=False):
         """detector.py:232-266 on [qn,h,w,3] in [0,1].  Returns channels-last maps."""
@@ -98,7 +116,7 @@ class Detector(PackedModule):
         maps = [br.run(i, lambda ht=ht, wt=wt: one_scale(ht, wt)) for i, (ht, wt) in enumerate(scales)]
         br.join()
         sizes = [[(r.shape[1], r.shape[2]) for r in raw] for raw in maps]
-        rfn = self.ref_kernels[0].cout
+        rfn = self.ref_center_feats[0].shape[0]
         feats = ops.det_score_fuse(maps, sizes, rfn, hs, ws, self.cfg['vgg_score_stats'], self.cfg['vgg_score_max'],
                                    p['w1'], p['b1'], p['w2'], p['b2'], qn)
         outs = {}

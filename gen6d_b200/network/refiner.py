@@ -200,11 +200,32 @@ class VolumeRefiner(PackedModule):
         return [self._ref_dev[i] for i in ids]
 
     def _refine_warped(self, size):
+        """jobs: per pose one query crop followed by its rfn reference crops (qn * (rfn + 1) records)."""
         def fn(jobs, que_K, que_pose, ref_Ks, ref_poses):
             n = jobs.numel() // ops.WARP_JOB_BYTES
-            crops = ops.warp_perspective_u8(jobs, n, size, size)
-            return self._refine_u8(crops[:1], que_K, que_pose, crops[1:][None], ref_Ks, ref_poses)
+            qn = que_K.shape[0]
+            crops = ops.warp_perspective_u8(jobs, n, size, size).reshape(qn, n // qn, size, size, 3)
+            return self._refine_u8(crops[:, 0].contiguous(), que_K, que_pose, crops[:, 1:].contiguous(), ref_Ks, ref_poses)
         return fn
+
+    def refine_batch(self, frames_dev, que_Ks, in_poses, size=128, ref_num=6, ref_even=False):
+        """refine_que_imgs for a batch of independent frames: the host geometry of refiner.py:285-325 per
+        frame, then ONE device stage for all of them (look-at crops cut from frames_dev[i] and the resident
+        database images, the feature net on qn*(rfn+1) crops, qn volumes, the 3-D stack on [qn,32,32,32,C]),
+        one D2H of [qn,7].  Returns the refined poses [qn,3,4] (identical to per-frame refine_que_imgs)."""
+        from .. import geometry as G
+        qn = len(in_poses)
+        probs = [G.refine_problem(self.ref_database, self.ref_ids, None, que_Ks[i], in_poses[i], size, ref_num, ref_even, warp=False)
+                 for i in range(qn)]
+        srcs, mats = [], []
+        for i, prob in enumerate(probs):
+            srcs += [frames_dev[i]] + self._ref_images_dev(list(prob['ref_ids']))
+            mats += [G.perspective_dst_to_src(prob['que_H'])] + [G.perspective_dst_to_src(H) for H in prob['ref_Hs']]
+        cams = ('que_K', 'que_pose', 'ref_Ks', 'ref_poses')
+        with torch.no_grad():
+            args = [self._to_dev(G.pack_warp_jobs(srcs, mats))] + [self._to_dev(np.stack([p[k] for p in probs], 0)) for k in cams]
+            out = self._to_host(self.stages.run(f'refine_warp{size}', self._refine_warped(size), args))
+        return np.stack([G.apply_refinement(prob, quat=o[:4], offset=o[4:6], scale=2.0 ** o[6]) for prob, o in zip(probs, out)], 0)
 
     def refine_que_imgs(self, que_img, que_K, in_pose, size=128, ref_num=6, ref_even=False, que_dev=None,
                         host_warps=False):

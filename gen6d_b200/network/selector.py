@@ -108,12 +108,13 @@ class ViewpointSelector(PackedModule):
         return cam / torch.clamp(torch.linalg.norm(cam, dim=1, keepdim=True), min=1e-12)
 
     def _load_nhwc(self, ref_norm4, rfn, an, ref_poses, object_center, object_vert, chunk=64):
-        """ref_norm4: [S = rfn*an (r-major), h, w, 4] ImageNet-normalised (selector.py:121-148).
-        With a sharded comm every rank is handed the full set and keeps references [r0, r1)."""
+        """ref_norm4: this rank's references [r0, r1) of the rfn in total, [S_local = (r1-r0)*an (r-major), h, w, 4]
+        ImageNet-normalised (selector.py:121-148); ref_poses are those of ALL rfn references.  The callers
+        slice the image set BEFORE it is uploaded / converted, so a rank never holds more than its shard."""
         p = self.packed()
         self.rfn_total = rfn
         r0, r1 = self.comm.shard_range(rfn)
-        ref_norm4 = ref_norm4[r0 * an:r1 * an]
+        assert ref_norm4.shape[0] == (r1 - r0) * an
         vp_all = self.viewpoints(ref_poses, object_center, object_vert)   # frame anchored on GLOBAL ref 0
         rfn = r1 - r0
         S = rfn * an
@@ -251,7 +252,8 @@ class ViewpointSelector(PackedModule):
             raise NotImplementedError('inference-only build: random forward-view selection is a training feature')
         with torch.no_grad():
             an, rfn, _, h, w = ref_imgs.shape
-            x = ref_imgs.permute(1, 0, 2, 3, 4).reshape(rfn * an, 3, h, w).float().contiguous()
+            r0, r1 = self.comm.shard_range(rfn)
+            x = ref_imgs[:, r0:r1].permute(1, 0, 2, 3, 4).reshape((r1 - r0) * an, 3, h, w).float().contiguous()
             x = ops.imagenet_norm(ops.nchw_to_nhwc(x), out_c=4)
             self._load_nhwc(x, rfn, an, ref_poses, object_center, object_vert)
 
@@ -274,7 +276,9 @@ class ViewpointSelector(PackedModule):
         (selector.py:150-163)"""
         with torch.no_grad():
             an, rfn, h, w, _ = ref_imgs.shape
-            u8 = self._to_dev(np.ascontiguousarray(ref_imgs.transpose(1, 0, 2, 3, 4))).reshape(rfn * an, h, w, 3)
+            r0, r1 = self.comm.shard_range(rfn)
+            u8 = torch.from_numpy(np.ascontiguousarray(ref_imgs[:, r0:r1].transpose(1, 0, 2, 3, 4))).to(self.device)
+            u8 = u8.reshape((r1 - r0) * an, h, w, 3)            # one-off load: no pinned staging ring for ~100s of MB
             x = ops.preprocess_u8(u8, out_c=4, imagenet_norm=True)
             self._load_nhwc(x, rfn, an, ref_poses.astype(np.float32), object_center.astype(np.float32),
                             object_vert.astype(np.float32))
@@ -298,6 +302,20 @@ class ViewpointSelector(PackedModule):
                 crop, idx, out, logits = self.stages.run(f'select_warp{size}', fn, [jobs])
             else:
                 crop, idx, out, logits = fn(jobs)           # collectives inside: run eagerly
+            crop, idx, out, logits = [self._to_host(t) for t in (crop, idx, out, logits)]
+        return {'ref_idx': idx, 'angles': out[:, 0].copy(), 'scores': logits, 'que_imgs': crop}
+
+    def select_from_frames(self, frames_dev, Ms, size):
+        """Batched select_from_frame: crop i is cut out of frames_dev[i] (uint8 [qn,h,w,3] on the device)
+        with the 2x3 similarity Ms[i]; one stage (one graph launch, one D2H) for the whole batch."""
+        from .. import geometry as G
+        fn = self._select_warped(size)
+        with torch.no_grad():
+            jobs = self._to_dev(G.pack_warp_jobs([frames_dev[i] for i in range(len(Ms))], [G.affine_dst_to_src(M) for M in Ms]))
+            if self.comm.world == 1:
+                crop, idx, out, logits = self.stages.run(f'select_warp{size}', fn, [jobs])
+            else:
+                crop, idx, out, logits = fn(jobs)
             crop, idx, out, logits = [self._to_host(t) for t in (crop, idx, out, logits)]
         return {'ref_idx': idx, 'angles': out[:, 0].copy(), 'scores': logits, 'que_imgs': crop}
 

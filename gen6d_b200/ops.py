@@ -214,7 +214,7 @@ def add(a, b):
 @dataclass
 class PackedConv:
     """Convolution weights in the library's [K, ldw] layout (+ bias), see g6d_pack_conv_weight."""
-    w: torch.Tensor
+    w: Optional[torch.Tensor]   # FFMA layout (None for tensor-core-only operands)
     bias: Optional[torch.Tensor]
     cin: int          # padded input channels the packed weight expects
     cout: int
@@ -224,6 +224,8 @@ class PackedConv:
     w_hi: Optional[torch.Tensor] = None   # tensor-core path: [rows, K] hi / lo operand split (K-major)
     w_lo: Optional[torch.Tensor] = None
     kind: int = _lib.TC_TF32              # container of w_hi / w_lo: TC_TF32 (fp32 arrays) or TC_F16 (half arrays)
+    rows: Optional[tuple] = None          # (k, rfn) of a row-decomposed detector correlation (see g6d_det_corr_rowsum)
+    max_chain_k: int = 0                  # > 0: bound on the K-elements per tensor-core accumulate chain (same-sign operands)
 
 
 def conv_path():
@@ -316,7 +318,7 @@ def conv(x, pc, prologue=PRO_NONE, pro_scale=None, pro_shift=None, group_rows=1,
         out = torch.empty(shape, device=x.device, dtype=torch.float32)
     d = _lib.ConvDesc(B=B, D=D, H=H, W=W, Cin=pc.cin, in_cstride=cs, in_coff=in_coff, Cout=pc.cout, kd=kd, kh=kh,
                       kw=kw, stride=s, pd=pd, ph=ph, pw=pw, Do=Do, Ho=Ho, Wo=Wo, out_cstride=out.shape[-1],
-                      out_coff=out_coff, prologue=prologue, group_rows=group_rows, act=act)
+                      out_coff=out_coff, prologue=prologue, group_rows=group_rows, act=act, max_chain_k=pc.max_chain_k)
     work = 2.0 * B * Do * Ho * Wo * pc.cout * kd * kh * kw * pc.cin
     if pc.w_hi is not None and conv_path() == 'tc' and _lib.lib().g6d_conv_tc_supported(C.byref(d), pc.kind):
         nbytes = _lib.lib().g6d_conv_tc_workspace_bytes(C.byref(d), pc.kind)
@@ -327,6 +329,8 @@ def conv(x, pc, prologue=PRO_NONE, pro_scale=None, pro_shift=None, group_rows=1,
               pc.kind, _p(pc.bias), _p(pro_scale), _p(pro_shift), _p(out), _p(ws), _stream(), work=work,
               tag=f'M={B * Do * Ho * Wo} N={pc.cout} K={kd * kh * kw * pc.cin} k={kd}x{kh}x{kw} s={s} pro={prologue}')
         return out
+    if pc.w is None:
+        raise _lib.Gen6DLibraryError('this operand was packed for the tensor-core path only and the problem is not supported there')
     nbytes = _lib.lib().g6d_conv_workspace_bytes(C.byref(d))
     if nbytes < 0:
         _lib.check(-1, 'g6d_conv_workspace_bytes')
@@ -360,6 +364,15 @@ def det_score_fuse(maps, sizes, rfn, hs, ws, stats, clip, w1, b1, w2, b2, qn):
     m.clip = float(clip)
     out = torch.empty(qn, hs, ws, 64, device=w1.device, dtype=torch.float32)
     _call('g6d_det_score_fuse', C.byref(m), qn, _p(w1), _p(b1), _p(w2), _p(b2), _p(out), _stream())
+    return out
+
+
+def det_corr_rowsum(partial, k, rfn):
+    """partial [qn, H+k-1, W, k*rfn] (1 x k convolution, channel = ky*rfn + r) -> k x k correlation [qn, H, W, rfn]."""
+    qn, Hp, W, _ = partial.shape
+    H = Hp - (k - 1)
+    out = torch.empty(qn, H, W, rfn, device=partial.device, dtype=torch.float32)
+    _call('g6d_det_corr_rowsum', _p(partial), _p(out), qn, H, W, k, rfn, _stream())
     return out
 
 
@@ -406,7 +419,7 @@ def sel_corr_score3(refs, qs):
     S, Cc = refs[0].shape[0], refs[0].shape[2]
     Ps = [r.shape[1] for r in refs]
     out = torch.empty(3, S, device=refs[0].device, dtype=torch.float32)
-    ws = torch.empty(S * sum(Ps), device=refs[0].device, dtype=torch.float32)
+    ws = torch.empty(_lib.lib().g6d_sel_corr_score3_workspace_bytes(S, *Ps) // 4, device=refs[0].device, dtype=torch.float32)
     _call('g6d_sel_corr_score3', _p(refs[0]), _p(refs[1]), _p(refs[2]), _p(qs[0]), _p(qs[1]), _p(qs[2]), S, Ps[0], Ps[1],
           Ps[2], Cc, _p(out), _p(ws), _stream(), work=4.0 * (S * sum(Ps) * Cc + sum(Ps) * Cc + 3 * S))
     return out

@@ -124,6 +124,10 @@ typedef struct g6d_conv_desc {
     int prologue;             /* G6D_PRO_* applied to in-bounds input elements before the MAC */
     long long group_rows;     /* G6D_PRO_AFFINE*: input batch items per norm group */
     int act;                  /* G6D_ACT_* epilogue after bias */
+    int max_chain_k;          /* tensor-core path: 0 = default; > 0 bounds the K-elements accumulated in one TMEM
+                                 chain (longer problems are split and summed in fp32 round-to-nearest).  The tensor
+                                 core truncates on every accumulate, which biases long chains of SAME-SIGN products
+                                 (detector correlation: post-ReLU features x post-ReLU features) by ~5e-8 per step. */
 } g6d_conv_desc;
 
 #define G6D_PRO_NONE 0
@@ -198,6 +202,12 @@ typedef struct g6d_det_maps {
  * over references).  w1 [64, 3S] (channel = scale*3 + level), w2 [64, 64].  out [qn, hs, ws, 64]. */
 int g6d_det_score_fuse(const g6d_det_maps* host_maps, int qn, const float* w1, const float* b1,
                        const float* w2, const float* b2, float* out, g6d_stream_t stream);
+/* Row-decomposed form of the sliding inner product of detector.py:222-224: with the reference features
+ * [rfn, k, k, C] packed as a 1 x k convolution of k*rfn output channels (channel = ky*rfn + r, zero
+ * padding k/2 in both axes, so the result has H + k - 1 rows), partial [qn, H+k-1, W, k*rfn] holds the
+ * contribution of kernel row ky to input row y'; out[q,y,x,r] = sum_ky partial[q, y+ky, x, ky*rfn + r]
+ * is the k x k correlation map [qn, H, W, rfn].  rfn % 4 == 0. */
+int g6d_det_corr_rowsum(const float* partial, float* out, int qn, int H, int W, int k, int rfn, g6d_stream_t stream);
 /* detector.py:85-121: first-max flat argmax of scores [qn,hs,ws,1], then
  * position = ((x,y) + offset[y,x] + 0.5)*pool - 0.5, scale = 2**scale[y,x].
  * out [qn, 4] = (x, y, scale, score); out_idx [qn] (int64 flat index y*ws + x). */
@@ -218,7 +228,10 @@ int g6d_sel_corr_prologue(const float* q, const double* sum1, const double* sum2
  * score[s] = sum_p s[p]^2 / max_p s[p].  ref [S, P, C] is streamed once from HBM. */
 int g6d_sel_corr_score(const float* ref, const float* q, int S, int P, int C, float* score, g6d_stream_t stream);
 /* The same score for the three pyramid levels in one streaming pass (what select_que_imgs uses):
- * score [3, S]; ws: S*(P0+P1+P2) floats (per-location inner products, L2-resident). */
+ * score [3, S]; ws: g6d_sel_corr_score3_workspace_bytes(S, P0, P1, P2) bytes (per-location inner
+ * products, L2-resident, + one completion counter per (level, slice): the warp that finishes the last
+ * location of a slice reduces it, so the whole op is one launch). */
+long long g6d_sel_corr_score3_workspace_bytes(int S, int P0, int P1, int P2);
 int g6d_sel_corr_score3(const float* ref0, const float* ref1, const float* ref2, const float* q0, const float* q1,
                         const float* q2, int S, int P0, int P1, int P2, int C, float* score, float* ws,
                         g6d_stream_t stream);

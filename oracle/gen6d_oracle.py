@@ -32,8 +32,8 @@ _VGG_BLOCKS = ((0,), (4,), (8, 11), (15, 18), (22, 25))
 
 def _img_norm(x):
     """torchvision Normalize(mean, std) on NCHW (network/detector.py:156,189)."""
-    mean = torch.tensor(IMAGENET_MEAN, dtype=x.dtype).view(1, 3, 1, 1)
-    std = torch.tensor(IMAGENET_STD, dtype=x.dtype).view(1, 3, 1, 1)
+    mean = torch.tensor(IMAGENET_MEAN, dtype=x.dtype, device=x.device).view(1, 3, 1, 1)
+    std = torch.tensor(IMAGENET_STD, dtype=x.dtype, device=x.device).view(1, 3, 1, 1)
     return (x - mean) / std
 
 
@@ -167,7 +167,7 @@ def det_parse(scores, scales, offsets, pool_ratio=8):
     qn, _, hq, wq = scores.shape
     idx = torch.argmax(scores.flatten(1), 1)
     ys, xs = idx // wq, idx % wq
-    ar = torch.arange(qn)
+    ar = torch.arange(qn, device=scores.device)
     pos = torch.stack([xs, ys], -1) + offsets[ar, :, ys, xs]
     pos = (pos + 0.5) * pool_ratio - 0.5
     return pos, 2 ** scales[ar, 0, ys, xs], idx
@@ -303,7 +303,7 @@ def sel_forward(sd, que_imgs, ref_feats, ref_pose_embed, return_taps=False):
 def sel_select(logits, angles):
     """select_que_imgs post-processing (selector.py:172-175)."""
     idx = torch.argmax(logits, 1)
-    return idx, angles[torch.arange(idx.shape[0]), idx]
+    return idx, angles[torch.arange(idx.shape[0], device=idx.device), idx]
 
 
 # ----------------------------------------------------------------------------------------------
@@ -343,7 +343,7 @@ def ref_sample_volume(feats, verts, projs, h_in, w_in):
 
 def ref_volume_coords(poses_in, sn):
     """Unit-cube grid rotated by the input pose (refiner.py:211-222): row vectors @ R_in."""
-    c = torch.linspace(-1, 1, sn, dtype=torch.float32)
+    c = torch.linspace(-1, 1, sn, dtype=torch.float32, device=poses_in.device)
     g = torch.stack(torch.meshgrid(c, c, c, indexing='ij'), -1).reshape(1, sn ** 3, 3)
     return g @ poses_in[:, :3, :3]  # qn, sn^3, 3
 

@@ -87,9 +87,26 @@ def test_tc_splitk_correlation(ops):
     ref = F.conv2d(q.double(), r.double(), padding=7).float()
     rk = r.permute(0, 2, 3, 1).contiguous().cuda()
     flat = rk.reshape(32, -1)
-    pc = ops.PackedConv(ops.transpose_to_packed(flat), None, 512, 32, (1, 15, 15), 1, (0, 7, 7))
+    pc = ops.PackedConv(ops.transpose_to_packed(flat), None, 512, 32, (1, 15, 15), 1, (0, 7, 7), max_chain_k=2048)
     pc.w_hi, pc.w_lo, pc.kind = ops.split_operand(flat, ops.tc_kind_for(512))
     y = nchw(ops.conv(nhwc(q), pc))
+    assert rel_err(y, ref) < 5e-6
+
+
+@pytest.mark.parametrize('k,rfn,H,W', [(15, 32, 12, 16), (7, 32, 9, 11), (3, 64, 6, 5)])
+def test_tc_row_decomposed_correlation(ops, k, rfn, H, W):
+    """The detector's sliding inner product as a 1 x k convolution with k*rfn output channels + the row sum
+    (g6d_det_corr_rowsum) equals F.conv2d with the k x k kernels (detector.py:222-224)."""
+    q = torch.randn(2, 512, H, W, generator=g(40)).abs()
+    r = torch.randn(rfn, 512, k, k, generator=g(41)).abs()
+    ref = F.conv2d(q.double(), r.double(), padding=k // 2).float()
+    f = r.permute(0, 2, 3, 1).contiguous().cuda()                       # [rfn, ky, kx, c] as the detector caches them
+    flat = f.permute(1, 0, 2, 3).reshape(k * rfn, k * 512).contiguous()
+    pc = ops.PackedConv(None, None, 512, k * rfn, (1, 1, k), 1, (0, k // 2, k // 2), max_chain_k=2048)
+    pc.w_hi, pc.w_lo, pc.kind = ops.split_operand(flat, ops.tc_kind_for(512))
+    part = ops.conv(nhwc(q), pc)
+    assert tuple(part.shape) == (2, H + k - 1, W, k * rfn)
+    y = nchw(ops.det_corr_rowsum(part, k, rfn))
     assert rel_err(y, ref) < 5e-6
 
 
