@@ -597,7 +597,9 @@ static int fill_tc_params(const g6d_conv_desc* d, int kind, ConvTcP& p) {
     // K chains of same-sign products (detector correlation: K = 115200 of post-ReLU features)
     // that is a systematic bias of ~4e-5 relative.  For long-K problems (K > 8192) the chain per
     // CTA is bounded to 2048 terms and the partials are summed in fp32 round-to-nearest.
-    const int chain = d->max_chain_k > 0 ? d->max_chain_k : (K > 8192 ? TC_MAX_K_PER_CHAIN : 0);
+    // d->max_chain_k bounds the K-elements per ACCUMULATOR; a split rotates over NMAIN of them
+    const int nmain = bn == 32 ? Tc2Cfg<32>::NMAIN : (bn == 64 ? Tc2Cfg<64>::NMAIN : Tc2Cfg<128>::NMAIN);
+    const int chain = d->max_chain_k > 0 ? d->max_chain_k * nmain : (K > 8192 ? TC_MAX_K_PER_CHAIN : 0);
     const int max_kb = chain > bk ? chain / bk : 1;
     const int min_splits = chain > 0 ? (p.kblocks + max_kb - 1) / max_kb : 1;
     splits = splits < min_splits ? min_splits : splits;
@@ -1014,7 +1016,8 @@ static int fill_flat_params(const g6d_conv_desc* d, int kind, ConvFlatP& p, int*
     const long long K = (long long)d->Cin * d->kd * d->kh * d->kw;
     int splits = 1;
     if (ctas < kNumSMs && p.cblocks >= 2) splits = (int)((kNumSMs + ctas - 1) / ctas);
-    const long long chain = d->max_chain_k > 0 ? d->max_chain_k : (K > 8192 ? TC_MAX_K_PER_CHAIN : 0);
+    const int nmain = bn == 32 ? FlatCfg<32>::NMAIN : (bn == 64 ? FlatCfg<64>::NMAIN : FlatCfg<128>::NMAIN);
+    const long long chain = d->max_chain_k > 0 ? (long long)d->max_chain_k * nmain : (K > 8192 ? TC_MAX_K_PER_CHAIN : 0);
     if (chain > 0) { const int ms = (int)((K + chain - 1) / chain); splits = splits < ms ? ms : splits; }
     splits = splits > p.cblocks ? p.cblocks : splits;
     splits = splits < 1 ? 1 : splits;

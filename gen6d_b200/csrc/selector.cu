@@ -92,16 +92,16 @@ __device__ __forceinline__ float row_dot(const float4* __restrict__ rp, const fl
     return t;
 }
 
-// FUSED: the warp that completes the last row pair of a (level, slice) item -- found with one
-// atomic counter per item -- also reduces that item's P inner products to the score, with the
-// reference's operation order (selector.py:192-194: s / max first, then sum of s * (s / max); IEEE
-// behaviour for max <= 0, no epsilon).  No second launch, no second pass over t from another kernel.
+// FUSED: every CTA streams one CONTIGUOUS chunk of rows, then (one __threadfence per warp, one
+// __syncthreads) adds the rows it contributed to each (level, slice) item it touched to that item's
+// completion counter; the CTA that completes an item reduces its P inner products to the score with
+// the reference's operation order (selector.py:192-194: s / max first, then sum of s * (s / max); IEEE
+// behaviour for max <= 0, no epsilon).  ~6 atomics per CTA, no second launch.
 template <int C, bool FUSED>
 __global__ void __launch_bounds__(256) sel_corr_dots_kernel(const ScoreLevels L, float* __restrict__ t_out,
-                                                            int* __restrict__ done, float* __restrict__ score) {
-    const int lane = threadIdx.x & 31;
-    const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+                                                            int* __restrict__ done, float* __restrict__ score,
+                                                            long long chunk) {
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const long long rows = L.row_end[2];
     auto locate = [&](long long row, const float4*& rp, const float4*& qp, int& item, int& P, long long& first) {
         // static selects (no dynamic indexing of the parameter struct -> no local-memory copy)
@@ -118,13 +118,23 @@ __global__ void __launch_bounds__(256) sel_corr_dots_kernel(const ScoreLevels L,
         rp = reinterpret_cast<const float4*>(ref + local * C);
         qp = reinterpret_cast<const float4*>(q + (long long)p * C);
     };
-    for (long long row = warp * 2; row < rows; row += nwarps * 2) {
+    long long begin, end, stride;
+    if (FUSED) {        // contiguous chunk per CTA, row pairs dealt to its 8 warps
+        begin = (long long)blockIdx.x * chunk;
+        end = min(rows, begin + chunk);
+        stride = 16;
+    } else {            // grid-stride over all rows
+        begin = 0; end = rows;
+        stride = (((long long)gridDim.x * blockDim.x) >> 5) * 2;
+    }
+    const long long w0 = FUSED ? wib : (((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+    for (long long row = begin + w0 * 2; row < end; row += stride) {
         const float4 *r0, *q0, *r1, *q1;
-        int item0, item1, P0, P1;
-        long long first0, first1;
-        locate(row, r0, q0, item0, P0, first0);
-        const bool two = row + 1 < rows;
-        locate(two ? row + 1 : row, r1, q1, item1, P1, first1);
+        int item, P;
+        long long first;
+        locate(row, r0, q0, item, P, first);
+        const bool two = row + 1 < end;
+        locate(two ? row + 1 : row, r1, q1, item, P, first);
         float t0 = row_dot<C>(r0, q0, lane);
         float t1 = row_dot<C>(r1, q1, lane);
         t0 = warp_sum(t0);
@@ -133,27 +143,25 @@ __global__ void __launch_bounds__(256) sel_corr_dots_kernel(const ScoreLevels L,
             t_out[row] = t0;
             if (two) t_out[row + 1] = t1;
         }
-        if (FUSED) {
-            // publish, count, and let the last arriver of each item finish it (a pair straddles two
-            // items only when P is odd; handled by counting the two rows separately)
-            int last0 = 0, last1 = 0;
-            if (lane == 0) {
-                __threadfence();
-                if (two && item1 == item0) {
-                    last0 = atomicAdd(done + item0, 2) + 2 == P0;
-                } else {
-                    last0 = atomicAdd(done + item0, 1) + 1 == P0;
-                    if (two) last1 = atomicAdd(done + item1, 1) + 1 == P1;
-                }
-            }
-            last0 = __shfl_sync(0xffffffffu, last0, 0);
-            last1 = __shfl_sync(0xffffffffu, last1, 0);
-#pragma unroll 1
-            for (int h = 0; h < 2; ++h) {
-                if (!(h == 0 ? last0 : last1)) continue;                 // warp-uniform
-                const int item = h == 0 ? item0 : item1, P = h == 0 ? P0 : P1;
-                const float* tp = t_out + (h == 0 ? first0 : first1);
-                __threadfence();                                         // acquire: the other warps' t values
+    }
+    if (!FUSED) return;
+    if (lane == 0) __threadfence();                // this warp's t values are visible device-wide ...
+    __syncthreads();                               // ... before any thread of the CTA counts them in
+    // the items this chunk overlaps, dealt round-robin to the warps
+    int n = 0;
+    for (long long r = begin; r < end; ++n) {
+        const float4 *rp, *qp;
+        int item, P;
+        long long first;
+        locate(r, rp, qp, item, P, first);
+        const long long next = min(end, first + P);
+        if ((n & 7) == wib) {
+            int last = 0;
+            if (lane == 0) last = atomicAdd(done + item, (int)(next - r)) + (int)(next - r) == P;
+            last = __shfl_sync(0xffffffffu, last, 0);
+            if (last) {                                                   // warp-uniform
+                __threadfence();                                          // acquire: the other CTAs' t values
+                const float* tp = t_out + first;
                 float m = -INFINITY;
                 for (int p = lane; p < P; p += 32) m = fmaxf(m, __ldcg(tp + p));
                 m = warp_max(m);
@@ -163,6 +171,7 @@ __global__ void __launch_bounds__(256) sel_corr_dots_kernel(const ScoreLevels L,
                 if (lane == 0) score[item] = acc;       // [3, S]
             }
         }
+        r = next;
     }
 }
 
@@ -385,11 +394,14 @@ extern "C" int g6d_sel_corr_score3(const float* ref0, const float* ref1, const f
     if (fused) {
         cudaError_t e = cudaMemsetAsync(done, 0, sizeof(int) * 3 * S, st);
         if (e != cudaSuccess) { set_error("g6d_sel_corr_score3: memset: %s", cudaGetErrorString(e)); return G6D_ECUDA; }
-        sel_corr_dots_kernel<512, true><<<(unsigned)grid, 256, 0, st>>>(L, ws, done, score);
+        long long chunk = (L.row_end[2] + grid - 1) / grid;
+        chunk += chunk & 1;                                  // even: row pairs never straddle two CTAs
+        grid = (L.row_end[2] + chunk - 1) / chunk;
+        sel_corr_dots_kernel<512, true><<<(unsigned)grid, 256, 0, st>>>(L, ws, done, score, chunk);
         G6D_CHECK_LAUNCH("g6d_sel_corr_score3");
         return G6D_OK;
     }
-    sel_corr_dots_kernel<512, false><<<(unsigned)grid, 256, 0, st>>>(L, ws, nullptr, nullptr);
+    sel_corr_dots_kernel<512, false><<<(unsigned)grid, 256, 0, st>>>(L, ws, nullptr, nullptr, 0);
     G6D_CHECK_LAUNCH("g6d_sel_corr_score3(dots)");
     sel_corr_finish_kernel<<<ceil_div(3ll * S * 32, 256), 256, 0, st>>>(L, ws, score);
     G6D_CHECK_LAUNCH("g6d_sel_corr_score3(finish)");

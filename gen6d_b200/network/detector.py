@@ -66,13 +66,13 @@ class Detector(PackedModule):
                 pc = ops.PackedConv(None, None, c, k * rfn, (1, 1, k), 1, (0, k // 2, k // 2))
                 pc.w_hi, pc.w_lo, pc.kind = ops.split_operand(flat, kind)
                 pc.rows = (k, rfn)
-                pc.max_chain_k = 2048        # post-ReLU features x post-ReLU features: same-sign products
+                pc.max_chain_k = 640        # post-ReLU features x post-ReLU features: same-sign products
             else:
                 flat = f.reshape(rfn, k * k * c)
                 pc = ops.PackedConv(ops.transpose_to_packed(flat), None, c, rfn, (1, k, k), 1, (0, k // 2, k // 2))
                 if rfn >= 16 and kind is not None:   # channels-last features [rfn, (ky,kx,c)] are already the K-major B operand
                     pc.w_hi, pc.w_lo, pc.kind = ops.split_operand(flat, kind)
-                    pc.max_chain_k = 2048
+                    pc.max_chain_k = 640
             kernels.append(pc)
         self.ref_kernels = kernels
         self.bump_generation()          # captured graphs / worker clones hold pointers to the previous reference set

@@ -124,8 +124,8 @@ typedef struct g6d_conv_desc {
     int prologue;             /* G6D_PRO_* applied to in-bounds input elements before the MAC */
     long long group_rows;     /* G6D_PRO_AFFINE*: input batch items per norm group */
     int act;                  /* G6D_ACT_* epilogue after bias */
-    int max_chain_k;          /* tensor-core path: 0 = default; > 0 bounds the K-elements accumulated in one TMEM
-                                 chain (longer problems are split and summed in fp32 round-to-nearest).  The tensor
+    int max_chain_k;          /* tensor-core path: 0 = default; > 0 bounds the K-elements accumulated into one TMEM
+                                 accumulator (longer problems are split and summed in fp32 round-to-nearest).  The tensor
                                  core truncates on every accumulate, which biases long chains of SAME-SIGN products
                                  (detector correlation: post-ReLU features x post-ReLU features) by ~5e-8 per step. */
 } g6d_conv_desc;

@@ -87,7 +87,7 @@ def test_tc_splitk_correlation(ops):
     ref = F.conv2d(q.double(), r.double(), padding=7).float()
     rk = r.permute(0, 2, 3, 1).contiguous().cuda()
     flat = rk.reshape(32, -1)
-    pc = ops.PackedConv(ops.transpose_to_packed(flat), None, 512, 32, (1, 15, 15), 1, (0, 7, 7), max_chain_k=2048)
+    pc = ops.PackedConv(ops.transpose_to_packed(flat), None, 512, 32, (1, 15, 15), 1, (0, 7, 7), max_chain_k=640)
     pc.w_hi, pc.w_lo, pc.kind = ops.split_operand(flat, ops.tc_kind_for(512))
     y = nchw(ops.conv(nhwc(q), pc))
     assert rel_err(y, ref) < 5e-6
@@ -102,7 +102,7 @@ def test_tc_row_decomposed_correlation(ops, k, rfn, H, W):
     ref = F.conv2d(q.double(), r.double(), padding=k // 2).float()
     f = r.permute(0, 2, 3, 1).contiguous().cuda()                       # [rfn, ky, kx, c] as the detector caches them
     flat = f.permute(1, 0, 2, 3).reshape(k * rfn, k * 512).contiguous()
-    pc = ops.PackedConv(None, None, 512, k * rfn, (1, 1, k), 1, (0, k // 2, k // 2), max_chain_k=2048)
+    pc = ops.PackedConv(None, None, 512, k * rfn, (1, 1, k), 1, (0, k // 2, k // 2), max_chain_k=640)
     pc.w_hi, pc.w_lo, pc.kind = ops.split_operand(flat, ops.tc_kind_for(512))
     part = ops.conv(nhwc(q), pc)
     assert tuple(part.shape) == (2, H + k - 1, W, k * rfn)
