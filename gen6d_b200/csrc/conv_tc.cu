@@ -70,6 +70,7 @@ struct ConvTcP {
     int B, D, H, W, Cin, ics, ico, Cout, kd, kh, kw, stride, pd, ph, pw, Do, Ho, Wo, ocs, oco, pro, act;
     long long group_rows;
     int M, K, kblocks, splits, kb_per_split;
+    double* stats; long long stats_rows;      // fused InstanceNorm statistics of the OUTPUT (see epilogue_stats)
 };
 
 // ------------------------------------------------------------------------------------------ operand split
@@ -155,6 +156,34 @@ __device__ __forceinline__ bool elect_one_sync() {
         : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),             \
           "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])        \
         : "r"(taddr))
+
+// Fused InstanceNorm statistics of the convolution's OUTPUT (the reference normalises the raw conv
+// result and the next layer's loader applies it): each epilogue warp holds 32 output rows x 16 channels
+// of final values; a transposing butterfly (8+4+2+1+1 shuffles per quantity) leaves the 32-row sums of
+// channel (lane >> 1) in lanes 2c / 2c+1; even lanes add sum(y), odd lanes sum(y^2) to the per
+// (group, channel) fp64 accumulators the separate in_stats_partial pass used to produce.  All 32 rows of
+// a warp belong to one group (the host only enables this when stats_rows % 32 == 0 / whole planes).
+__device__ __forceinline__ void epilogue_stats(float (&v)[16], bool row_valid, double* __restrict__ ws, long long group,
+                                               int Cout, int n0, int lane) {
+    float q[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) { v[j] = row_valid ? v[j] : 0.f; q[j] = v[j] * v[j]; }
+#pragma unroll
+    for (int half = 8, off = 16; half >= 1; half >>= 1, off >>= 1) {
+        const bool upper = (lane & off) != 0;
+#pragma unroll
+        for (int j = 0; j < half; ++j) {
+            const float sv = upper ? v[j] : v[j + half], kv = upper ? v[j + half] : v[j];
+            const float sq = upper ? q[j] : q[j + half], kq = upper ? q[j + half] : q[j];
+            v[j] = kv + __shfl_xor_sync(0xffffffffu, sv, off);
+            q[j] = kq + __shfl_xor_sync(0xffffffffu, sq, off);
+        }
+    }
+    const float s1 = v[0] + __shfl_xor_sync(0xffffffffu, v[0], 1);
+    const float s2 = q[0] + __shfl_xor_sync(0xffffffffu, q[0], 1);
+    const int n = n0 + (lane >> 1);
+    if (n < Cout) atomicAdd(ws + (group * Cout + n) * 2 + (lane & 1), (double)((lane & 1) ? s2 : s1));
+}
 
 // ==========================================================================================
 // conv_tc2_kernel: persistent implicit-GEMM convolution.
@@ -455,38 +484,30 @@ conv_tc2_kernel(const ConvTcP p, const Tc2Work wk, const __grid_constant__ CUten
                         for (int j = 0; j < 16; ++j) accv[j] += __uint_as_float(r[j]);
                     }
                 }
-                if (m < p.M) {
-                    const int n0 = n_base + cc;
-                    float* dst = partial ? p.ws + ((long long)sp * p.M + m) * p.Cout + n0
-                                         : p.y + (long long)m * p.ocs + p.oco + n0;
-                    const bool vec = vec_ok && n0 + 16 <= p.Cout;
-                    if (vec) {      // 4 x 128-bit stores per thread instead of 16 scalar ones
+                const int n0 = n_base + cc;
+                if (!partial) {
 #pragma unroll
-                        for (int j4 = 0; j4 < 4; ++j4) {
-                            float4 v = make_float4(accv[j4 * 4], accv[j4 * 4 + 1], accv[j4 * 4 + 2], accv[j4 * 4 + 3]);
-                            if (!partial) {
-                                if (p.bias) {
-                                    const float4 bb = __ldg(reinterpret_cast<const float4*>(p.bias + n0) + j4);
-                                    v.x += bb.x; v.y += bb.y; v.z += bb.z; v.w += bb.w;
-                                }
-                                v.x = tc_act(v.x, p.act); v.y = tc_act(v.y, p.act); v.z = tc_act(v.z, p.act); v.w = tc_act(v.w, p.act);
-                            }
-                            reinterpret_cast<float4*>(dst)[j4] = v;
-                        }
-                    } else {
-#pragma unroll
-                        for (int j = 0; j < 16; ++j) {
-                            if (n0 + j < p.Cout) {
-                                float v = accv[j];
-                                if (!partial) {
-                                    if (p.bias) v += __ldg(p.bias + n0 + j);
-                                    v = tc_act(v, p.act);
-                                }
-                                dst[j] = v;
-                            }
-                        }
+                    for (int j = 0; j < 16; ++j) {
+                        float v = accv[j];
+                        if (p.bias && n0 + j < p.Cout) v += __ldg(p.bias + n0 + j);
+                        accv[j] = tc_act(v, p.act);
                     }
                 }
+                if (m < p.M) {
+                    float* dst = partial ? p.ws + ((long long)sp * p.M + m) * p.Cout + n0
+                                         : p.y + (long long)m * p.ocs + p.oco + n0;
+                    if (vec_ok && n0 + 16 <= p.Cout) {      // 4 x 128-bit stores per thread instead of 16 scalar ones
+#pragma unroll
+                        for (int j4 = 0; j4 < 4; ++j4)
+                            reinterpret_cast<float4*>(dst)[j4] = make_float4(accv[j4 * 4], accv[j4 * 4 + 1], accv[j4 * 4 + 2], accv[j4 * 4 + 3]);
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j)
+                            if (n0 + j < p.Cout) dst[j] = accv[j];
+                    }
+                }
+                if (p.stats && !partial)
+                    epilogue_stats(accv, m < p.M, p.stats, (long long)(mt * TC_BM + quad * 32) / p.stats_rows, p.Cout, n0, lane);
             }
             tc_fence_before();
             __syncwarp();
@@ -500,16 +521,31 @@ conv_tc2_kernel(const ConvTcP p, const Tc2Work wk, const __grid_constant__ CUten
     }
 }
 
-__global__ void conv_tc_reduce_kernel(const float* __restrict__ ws, const float* __restrict__ bias,
-                                      float* __restrict__ y, int M, int Cout, int splits, int ocs, int oco, int act) {
-    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= (long long)M * Cout) return;
-    const int n = (int)(i % Cout);
-    const long long m = i / Cout;
-    float v = 0.f;
-    for (int s = 0; s < splits; ++s) v += ws[(long long)s * M * Cout + i];
-    if (bias) v += bias[n];
-    y[m * ocs + oco + n] = tc_act(v, act);
+// Split-K epilogue: y = act(sum_s ws[s] + bias), and (optionally) the fused InstanceNorm statistics of y.
+// Block = 32 consecutive output rows (one group: stats_rows % 32 == 0), thread = channel (strided).
+__global__ void __launch_bounds__(256) conv_tc_reduce_kernel(const float* __restrict__ ws, const float* __restrict__ bias,
+                                                             float* __restrict__ y, int M, int Cout, int splits, int ocs, int oco,
+                                                             int act, double* __restrict__ stats, long long stats_rows) {
+    const int m0 = blockIdx.x * 32;
+    const int m1 = min(M, m0 + 32);
+    const long long slab = (long long)M * Cout;
+    for (int n = threadIdx.x; n < Cout; n += blockDim.x) {
+        const float b = bias ? bias[n] : 0.f;
+        float s1 = 0.f, s2 = 0.f;
+        for (int m = m0; m < m1; ++m) {
+            const long long i = (long long)m * Cout + n;
+            float v = 0.f;
+            for (int s = 0; s < splits; ++s) v += ws[(long long)s * slab + i];
+            v = tc_act(v + b, act);
+            y[(long long)m * ocs + oco + n] = v;
+            s1 += v; s2 = fmaf(v, v, s2);
+        }
+        if (stats) {
+            double* dst = stats + ((long long)(m0 / stats_rows) * Cout + n) * 2;
+            atomicAdd(dst, (double)s1);
+            atomicAdd(dst + 1, (double)s2);
+        }
+    }
 }
 
 // ------------------------------------------------------------------------------------------ host
@@ -694,6 +730,7 @@ struct ConvFlatP {
     long long group_rows;
     int Wp, tiles_per_plane, mode, nseg, taps_per_seg, seg_rows, rows_pad, ntab, cblocks;
     int a_stages, b_stages, splits, cb_per_split, M;
+    double* stats; long long stats_rows;
 };
 
 template <int BN> struct FlatCfg {
@@ -869,36 +906,29 @@ conv_tcflat_kernel(const ConvFlatP p, const __grid_constant__ CUtensorMap map_hi
                     for (int j = 0; j < 16; ++j) accv[j] += __uint_as_float(r[j]);
                 }
             }
+            const int n0 = n_base + col0 + cc;
+            if (!partial) {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    float v = accv[j];
+                    if (p.bias && n0 + j < p.Cout) v += __ldg(p.bias + n0 + j);
+                    accv[j] = tc_act(v, p.act);
+                }
+            }
             if (valid) {
-                const int n0 = n_base + col0 + cc;
                 float* dst = partial ? p.ws + ((long long)split * p.M + m) * p.Cout + n0 : p.y + m * p.ocs + p.oco + n0;
                 if (vec_ok && n0 + 16 <= p.Cout) {
 #pragma unroll
-                    for (int j4 = 0; j4 < 4; ++j4) {
-                        float4 v = make_float4(accv[j4 * 4], accv[j4 * 4 + 1], accv[j4 * 4 + 2], accv[j4 * 4 + 3]);
-                        if (!partial) {
-                            if (p.bias) {
-                                const float4 bb = __ldg(reinterpret_cast<const float4*>(p.bias + n0) + j4);
-                                v.x += bb.x; v.y += bb.y; v.z += bb.z; v.w += bb.w;
-                            }
-                            v.x = tc_act(v.x, p.act); v.y = tc_act(v.y, p.act); v.z = tc_act(v.z, p.act); v.w = tc_act(v.w, p.act);
-                        }
-                        reinterpret_cast<float4*>(dst)[j4] = v;
-                    }
+                    for (int j4 = 0; j4 < 4; ++j4)
+                        reinterpret_cast<float4*>(dst)[j4] = make_float4(accv[j4 * 4], accv[j4 * 4 + 1], accv[j4 * 4 + 2], accv[j4 * 4 + 3]);
                 } else {
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) {
-                        if (n0 + j < p.Cout) {
-                            float v = accv[j];
-                            if (!partial) {
-                                if (p.bias) v += __ldg(p.bias + n0 + j);
-                                v = tc_act(v, p.act);
-                            }
-                            dst[j] = v;
-                        }
-                    }
+                    for (int j = 0; j < 16; ++j)
+                        if (n0 + j < p.Cout) dst[j] = accv[j];
                 }
             }
+            if (p.stats && !partial)      // tiles never span planes and a group is made of whole planes
+                epilogue_stats(accv, valid, p.stats, (((long long)b * p.Do + zo) * p.Ho * p.Wo) / p.stats_rows, p.Cout, n0, lane);
         }
         tc_fence_before();
     } else if (warp == TC_PRODUCER_WARPS) {
@@ -1088,10 +1118,30 @@ extern "C" long long g6d_conv_tc_workspace_bytes(const g6d_conv_desc* desc, int 
     return p.splits > 1 ? (long long)p.splits * p.M * p.Cout * (long long)sizeof(float) : 0;
 }
 
+// fused output statistics are possible when every 32-row epilogue slice lies in one group
+static bool stats_ok_tc2(long long stats_rows, long long M) { return stats_rows > 0 && stats_rows % 32 == 0 && M % stats_rows == 0; }
+static bool stats_ok_flat(const ConvFlatP& fp, long long stats_rows) {
+    return stats_rows > 0 && stats_rows % 32 == 0 && stats_rows % ((long long)fp.Ho * fp.Wo) == 0 && (long long)fp.M % stats_rows == 0;
+}
+
+extern "C" int g6d_conv_tc_stats_supported(const g6d_conv_desc* desc, int kind, long long stats_rows) {
+    if (!g6d_conv_tc_supported(desc, kind)) return 0;
+    ConvFlatP fp{}; int smem = 0;
+    if (!flat_disabled() && fill_flat_params(desc, kind, fp, &smem) == 0) return stats_ok_flat(fp, stats_rows) ? 1 : 0;
+    const long long M = (long long)desc->B * desc->Do * desc->Ho * desc->Wo;
+    return stats_ok_tc2(stats_rows, M) ? 1 : 0;
+}
+
 extern "C" int g6d_conv_tc(const g6d_conv_desc* desc, const float* x, const void* w_hi, const void* w_lo, int w_rows,
                            int kind, const float* bias, const float* pro_scale, const float* pro_shift, float* y,
-                           void* ws, g6d_stream_t stream) {
+                           void* ws, double* stats, long long stats_rows, g6d_stream_t stream) {
     G6D_REQUIRE(kind == G6D_TC_TF32 || kind == G6D_TC_F16, "g6d_conv_tc: bad operand kind %d", kind);
+    if (stats) {
+        G6D_REQUIRE(g6d_conv_tc_stats_supported(desc, kind, stats_rows), "g6d_conv_tc: fused statistics need groups of whole 32-row slices / planes (stats_rows %lld)", stats_rows);
+        const long long M = (long long)desc->B * desc->Do * desc->Ho * desc->Wo;
+        cudaError_t e = cudaMemsetAsync(stats, 0, sizeof(double) * 2 * (M / stats_rows) * desc->Cout, as_stream(stream));
+        if (e != cudaSuccess) { set_error("g6d_conv_tc: memset: %s", cudaGetErrorString(e)); return G6D_ECUDA; }
+    }
     {   // stride-1 multi-tap convolutions: A-reuse kernel
         ConvFlatP fp{}; int smem = 0;
         if (!flat_disabled() && fill_flat_params(desc, kind, fp, &smem) == 0) {
@@ -1100,6 +1150,7 @@ extern "C" int g6d_conv_tc(const g6d_conv_desc* desc, const float* x, const void
             if (fp.pro != G6D_PRO_NONE) G6D_REQUIRE(pro_scale && pro_shift, "g6d_conv_tc: prologue operands missing");
             if (fp.splits > 1) G6D_REQUIRE(ws != nullptr, "g6d_conv_tc: split workspace required (%d splits)", fp.splits);
             fp.x = x; fp.bias = bias; fp.ps = pro_scale; fp.pb = pro_shift; fp.y = y; fp.ws = (float*)ws;
+            fp.stats = stats; fp.stats_rows = stats ? stats_rows : 1;
             const int bn = tc_block_n(fp.Cout);
             const int K = fp.kd * fp.kh * fp.kw * fp.Cin;
             CUtensorMap mh, ml;
@@ -1112,7 +1163,9 @@ extern "C" int g6d_conv_tc(const g6d_conv_desc* desc, const float* x, const void
             if (rc2 != G6D_OK) return rc2;
             if (fp.splits > 1) {
                 const long long n = (long long)fp.M * fp.Cout;
-                conv_tc_reduce_kernel<<<ceil_div(n, 256), 256, 0, st>>>(fp.ws, bias, y, fp.M, fp.Cout, fp.splits, fp.ocs, fp.oco, fp.act);
+                (void)n;
+                conv_tc_reduce_kernel<<<ceil_div(fp.M, 32), fp.Cout >= 256 ? 256 : (fp.Cout >= 128 ? 128 : 64), 0, st>>>(
+                    fp.ws, bias, y, fp.M, fp.Cout, fp.splits, fp.ocs, fp.oco, fp.act, fp.stats, fp.stats_rows);
                 G6D_CHECK_LAUNCH("g6d_conv_tc(flat reduce)");
             }
             return G6D_OK;
@@ -1126,6 +1179,7 @@ extern "C" int g6d_conv_tc(const g6d_conv_desc* desc, const float* x, const void
     if (p.pro != G6D_PRO_NONE) G6D_REQUIRE(pro_scale && pro_shift, "g6d_conv_tc: prologue operands missing");
     if (p.splits > 1) G6D_REQUIRE(ws != nullptr, "g6d_conv_tc: split-K workspace required (%d splits)", p.splits);
     p.x = x; p.bias = bias; p.ps = pro_scale; p.pb = pro_shift; p.y = y; p.ws = (float*)ws;
+    p.stats = stats; p.stats_rows = stats ? stats_rows : 1;
     const int bn = tc_block_n(p.Cout);
     CUtensorMap mh, ml;
     if ((rc = make_weight_map(&mh, w_hi, w_rows, p.K, bn, kind)) != G6D_OK) return rc;
@@ -1135,7 +1189,9 @@ extern "C" int g6d_conv_tc(const g6d_conv_desc* desc, const float* x, const void
     if (rc != G6D_OK) return rc;
     if (p.splits > 1) {
         const long long n = (long long)p.M * p.Cout;
-        conv_tc_reduce_kernel<<<ceil_div(n, 256), 256, 0, st>>>(p.ws, bias, y, p.M, p.Cout, p.splits, p.ocs, p.oco, p.act);
+        (void)n;
+        conv_tc_reduce_kernel<<<ceil_div(p.M, 32), p.Cout >= 256 ? 256 : (p.Cout >= 128 ? 128 : 64), 0, st>>>(
+            p.ws, bias, y, p.M, p.Cout, p.splits, p.ocs, p.oco, p.act, p.stats, p.stats_rows);
         G6D_CHECK_LAUNCH("g6d_conv_tc(splitk reduce)");
     }
     return G6D_OK;

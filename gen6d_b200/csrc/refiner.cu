@@ -180,7 +180,7 @@ __device__ __forceinline__ float4 ldg_at(const float* base, int idx) {
     return __ldg(reinterpret_cast<const float4*>(a));
 }
 template <int RT>
-__global__ void __launch_bounds__(256, 3) ref_volume_fill_c128_kernel(const VolParams p) {
+__global__ void __launch_bounds__(256, 2) ref_volume_fill_c128_kernel(const VolParams p) {
     constexpr int C = 128;
     constexpr int NV = RT + 1;                    // views: RT references + the query
     __shared__ float sP[NV][12];

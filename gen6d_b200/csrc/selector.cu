@@ -98,7 +98,7 @@ __device__ __forceinline__ float row_dot(const float4* __restrict__ rp, const fl
 // the reference's operation order (selector.py:192-194: s / max first, then sum of s * (s / max); IEEE
 // behaviour for max <= 0, no epsilon).  ~6 atomics per CTA, no second launch.
 template <int C, bool FUSED>
-__global__ void __launch_bounds__(256) sel_corr_dots_kernel(const ScoreLevels L, float* __restrict__ t_out,
+__global__ void __launch_bounds__(256, 6) sel_corr_dots_kernel(const ScoreLevels L, float* __restrict__ t_out,
                                                             int* __restrict__ done, float* __restrict__ score,
                                                             long long chunk) {
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
@@ -383,14 +383,22 @@ extern "C" int g6d_sel_corr_score3(const float* ref0, const float* ref1, const f
     L.row_end[0] = (long long)S * P0; L.row_end[1] = L.row_end[0] + (long long)S * P1;
     L.row_end[2] = L.row_end[1] + (long long)S * P2;
     cudaStream_t st = as_stream(stream);
+    static int fused = -1;
+    if (fused < 0) { const char* e = getenv("G6D_S2_FUSED"); fused = (e && e[0] == '0') ? 0 : 1; }
+    // one wave: as many CTAs per SM as are actually resident (the chunked kernel must not need a second wave)
+    static int occ[2] = {0, 0};
+    if (occ[fused] == 0) {
+        int n = 0;
+        cudaError_t e = fused ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, sel_corr_dots_kernel<512, true>, 256, 0)
+                              : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, sel_corr_dots_kernel<512, false>, 256, 0);
+        occ[fused] = (e == cudaSuccess && n > 0) ? n : 4;
+    }
     const long long pairs = (L.row_end[2] + 1) / 2;
     long long grid = (pairs + 7) / 8;                    // 8 warps per CTA, one row pair per warp per trip
-    const long long full = 8ll * kNumSMs;                // 8 CTAs x 256 threads = 64 warps per SM
+    const long long full = (long long)occ[fused] * kNumSMs;
     if (grid > full) grid = full;
     // workspace: [rows] floats of per-location inner products, then 3*S completion counters
     int* done = reinterpret_cast<int*>(ws + ((L.row_end[2] + 3) / 4) * 4);
-    static int fused = -1;
-    if (fused < 0) { const char* e = getenv("G6D_S2_FUSED"); fused = (e && e[0] == '0') ? 0 : 1; }
     if (fused) {
         cudaError_t e = cudaMemsetAsync(done, 0, sizeof(int) * 3 * S, st);
         if (e != cudaSuccess) { set_error("g6d_sel_corr_score3: memset: %s", cudaGetErrorString(e)); return G6D_ECUDA; }

@@ -64,10 +64,10 @@ class VolumeRefiner(PackedModule):
     # ------------------------------------------------------------------ cores (channels-last)
     def _conv_in_conv(self, x, pcs, rows_per_img):
         """conv -> InstanceNorm -> ReLU -> conv -> InstanceNorm (stats returned, not applied)."""
-        y = ops.conv(x, pcs[0])
-        ps, pb = ops.instnorm_stats(y, rows_per_group=rows_per_img, eps=IN_EPS)
-        y = ops.conv(y, pcs[1], prologue=ops.PRO_AFFINE_RELU, pro_scale=ps, pro_shift=pb, group_rows=1)
-        ps, pb = ops.instnorm_stats(y, rows_per_group=rows_per_img, eps=IN_EPS)
+        y, ws = ops.conv(x, pcs[0], stats_rows=rows_per_img)          # moments fused into the conv epilogue
+        ps, pb = ops.instnorm_finalize(ws, rows_per_img, IN_EPS)
+        y, ws = ops.conv(y, pcs[1], prologue=ops.PRO_AFFINE_RELU, pro_scale=ps, pro_shift=pb, group_rows=1, stats_rows=rows_per_img)
+        ps, pb = ops.instnorm_finalize(ws, rows_per_img, IN_EPS)
         return y, ps, pb
 
     def _feature_net(self, imgs_norm4):
@@ -103,8 +103,8 @@ class VolumeRefiner(PackedModule):
         br, keep = Branches(2), []
 
         def one_embed(bi, name, x):
-            y = ops.conv(x, p[name][0])
-            ps, pb = ops.instnorm_stats(y, rows_per_group=sn ** 3, eps=IN_EPS)
+            y, ws = ops.conv(x, p[name][0], stats_rows=sn ** 3)
+            ps, pb = ops.instnorm_finalize(ws, sn ** 3, IN_EPS)
             ops.conv(y, p[name][1], prologue=ops.PRO_AFFINE_RELU, pro_scale=ps, pro_shift=pb, group_rows=1,
                      out=cat, out_coff=64 * bi)
             keep.append((y, ps, pb))
@@ -114,8 +114,9 @@ class VolumeRefiner(PackedModule):
         br.join()
         x, pro, ps, pb = cat, ops.PRO_NONE, None, None
         for pc in p['trunk']:
-            y = ops.conv(x, pc, prologue=pro, pro_scale=ps, pro_shift=pb, group_rows=1)
-            ps, pb = ops.instnorm_stats(y, rows_per_group=y.shape[1] * y.shape[2] * y.shape[3], eps=IN_EPS)
+            vox = ((x.shape[1] - 1) // pc.stride + 1) ** 3                  # output voxels per pose (k 3, pad 1)
+            y, ws = ops.conv(x, pc, prologue=pro, pro_scale=ps, pro_shift=pb, group_rows=1, stats_rows=vox)
+            ps, pb = ops.instnorm_finalize(ws, vox, IN_EPS)
             x, pro = y, ops.PRO_AFFINE_RELU
         return ops.conv(x, p['conv5_3'], prologue=pro, pro_scale=ps, pro_shift=pb, group_rows=1)
 

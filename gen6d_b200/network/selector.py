@@ -135,13 +135,11 @@ class ViewpointSelector(PackedModule):
         self.ref_pose_embed = x.reshape(rfn, 512)
         self.bump_generation()          # captured graphs / worker clones hold pointers to the previous reference set
 
-    def _stats(self, y, rows_local, rows_total):
-        """InstanceNorm statistics over a group that may span GPUs: local (sum, sum-of-squares) in
-        fp64, all-reduced, then scale = rstd, shift = -mean*rstd (exact, not per-shard)."""
-        if self.comm.world == 1:
-            return ops.instnorm_stats(y, rows_per_group=rows_local, eps=IN_EPS)
-        ws = self.comm.all_reduce_sum(ops.instnorm_partial(y, rows_per_group=rows_local))
-        return ops.instnorm_finalize(ws, rows_total, IN_EPS)
+    def _finalize(self, ws, rows_total):
+        """InstanceNorm scale / shift from the (sum, sum-of-squares) moments a convolution's epilogue
+        produced (fp64).  The group may span GPUs: the moments are all-reduced first, so the statistics are
+        exact, not per-shard."""
+        return ops.instnorm_finalize(self.comm.all_reduce_sum(ws), rows_total, IN_EPS)
 
     def _tower(self, level, ref, scale, shift, cat_buf, S):
         """corr_conv_list[level] (selector.py:27-69) on the implicit correlation volume."""
@@ -149,15 +147,15 @@ class ViewpointSelector(PackedModule):
         x, pro, ps, pb = ref, ops.PRO_CORR, scale, shift
         for i, (pc, post) in enumerate(convs):
             last = i + 1 == len(convs)
-            y = ops.conv(x, pc, prologue=pro, pro_scale=ps, pro_shift=pb, group_rows=S,
-                         out=cat_buf if last else None, out_coff=256 * level if last else 0)
             if last:
+                ops.conv(x, pc, prologue=pro, pro_scale=ps, pro_shift=pb, group_rows=S, out=cat_buf, out_coff=256 * level)
                 break
+            rows = x.shape[0] * x.shape[1] * x.shape[2]                   # stride-1 same-size convolution
+            y, ws = ops.conv(x, pc, prologue=pro, pro_scale=ps, pro_shift=pb, group_rows=S, stats_rows=rows)
             # InstanceNorm3d statistics over (S, h, w) of the raw conv output; the normalisation
             # itself (and the ReLU) is applied by the next conv's loader.  MaxPool commutes with
             # the positive-slope affine, so pooling the raw tensor first is exact.
-            rows = y.numel() // y.shape[-1]
-            ps, pb = self._stats(y, rows, rows // self.ref_shape[0] * self.rfn_total)
+            ps, pb = self._finalize(ws, rows // self.ref_shape[0] * self.rfn_total)
             pro = ops.PRO_AFFINE_RELU if 'r' in post else ops.PRO_AFFINE
             x = ops.maxpool2x2(y) if 'p' in post else y
 
@@ -186,8 +184,8 @@ class ViewpointSelector(PackedModule):
         br.join()
         # corr_feats_conv (selector.py:71-77): 1x1 768->512, IN, ReLU, 1x1 512->512, AvgPool(4,4).
         # The second 1x1 conv is linear, so the 4x4 average is taken first (16x less work).
-        y = ops.conv(cat_buf, p['cf0'])
-        ps, pb = self._stats(y, S * 16, S_total * 16)
+        y, ws = ops.conv(cat_buf, p['cf0'], stats_rows=S * 16)
+        ps, pb = self._finalize(ws, S_total * 16)
         y = ops.avgpool_affine(y.reshape(S * 16, 512), 16, ps, pb, rows_per_group=S * 16, act=ops.ACT_RELU)
         ops.conv(y.reshape(S, 1, 1, 512), p['cf3'], out=feats.reshape(S, 1, 1, FEAT_PAD), out_coff=0)
         if self.comm.world == 1:

@@ -301,8 +301,12 @@ def transpose_to_packed(x2d):
 
 
 def conv(x, pc, prologue=PRO_NONE, pro_scale=None, pro_shift=None, group_rows=1, act=ACT_NONE,
-         in_coff=0, out=None, out_coff=0):
-    """x [B, D, H, W, cs] or [B, H, W, cs]; returns [B, Do, Ho, Wo, Cout] (or 4-D for 4-D input)."""
+         in_coff=0, out=None, out_coff=0, stats_rows=None):
+    """x [B, D, H, W, cs] or [B, H, W, cs]; returns [B, Do, Ho, Wo, Cout] (or 4-D for 4-D input).
+    stats_rows: also return the InstanceNorm moments of the OUTPUT, (y, ws) with ws float64
+    [groups, Cout, 2] = per group of `stats_rows` consecutive output rows (sum y, sum y^2) -- fused into the
+    convolution's epilogue on the tensor-core path (no extra pass over y), else by g6d_instnorm_partial;
+    pass ws to instnorm_finalize (after any cross-GPU all-reduce)."""
     four = x.dim() == 4
     if four:
         B, H, W, cs = x.shape
@@ -320,24 +324,40 @@ def conv(x, pc, prologue=PRO_NONE, pro_scale=None, pro_shift=None, group_rows=1,
                       kw=kw, stride=s, pd=pd, ph=ph, pw=pw, Do=Do, Ho=Ho, Wo=Wo, out_cstride=out.shape[-1],
                       out_coff=out_coff, prologue=prologue, group_rows=group_rows, act=act, max_chain_k=pc.max_chain_k)
     work = 2.0 * B * Do * Ho * Wo * pc.cout * kd * kh * kw * pc.cin
+    M = B * Do * Ho * Wo
+    stats = None
     if pc.w_hi is not None and conv_path() == 'tc' and _lib.lib().g6d_conv_tc_supported(C.byref(d), pc.kind):
         nbytes = _lib.lib().g6d_conv_tc_workspace_bytes(C.byref(d), pc.kind)
         if nbytes < 0:
             _lib.check(-1, 'g6d_conv_tc_workspace_bytes')
         ws = torch.empty(nbytes // 4, device=x.device, dtype=torch.float32) if nbytes > 0 else None
+        fuse = (stats_rows is not None and fused_stats_enabled() and
+                _lib.lib().g6d_conv_tc_stats_supported(C.byref(d), pc.kind, stats_rows))
+        if fuse:
+            stats = torch.empty(M // stats_rows, pc.cout, 2, device=x.device, dtype=torch.float64)
         _call('g6d_conv_tc', C.byref(d), _p(x), _p(pc.w_hi, pc.w_hi.dtype), _p(pc.w_lo, pc.w_lo.dtype), pc.w_hi.shape[0],
-              pc.kind, _p(pc.bias), _p(pro_scale), _p(pro_shift), _p(out), _p(ws), _stream(), work=work,
-              tag=f'M={B * Do * Ho * Wo} N={pc.cout} K={kd * kh * kw * pc.cin} k={kd}x{kh}x{kw} s={s} pro={prologue}')
+              pc.kind, _p(pc.bias), _p(pro_scale), _p(pro_shift), _p(out), _p(ws), _p(stats, torch.float64), stats_rows or 0,
+              _stream(), work=work,
+              tag=f'M={M} N={pc.cout} K={kd * kh * kw * pc.cin} k={kd}x{kh}x{kw} s={s} pro={prologue}')
+    else:
+        if pc.w is None:
+            raise _lib.Gen6DLibraryError('this operand was packed for the tensor-core path only and the problem is not supported there')
+        nbytes = _lib.lib().g6d_conv_workspace_bytes(C.byref(d))
+        if nbytes < 0:
+            _lib.check(-1, 'g6d_conv_workspace_bytes')
+        ws = torch.empty(nbytes // 4, device=x.device, dtype=torch.float32) if nbytes > 0 else None
+        _call('g6d_conv', C.byref(d), _p(x), _p(pc.w), _p(pc.bias), _p(pro_scale), _p(pro_shift), _p(out), _p(ws), _stream(),
+              work=work)
+    if stats_rows is None:
         return out
-    if pc.w is None:
-        raise _lib.Gen6DLibraryError('this operand was packed for the tensor-core path only and the problem is not supported there')
-    nbytes = _lib.lib().g6d_conv_workspace_bytes(C.byref(d))
-    if nbytes < 0:
-        _lib.check(-1, 'g6d_conv_workspace_bytes')
-    ws = torch.empty(nbytes // 4, device=x.device, dtype=torch.float32) if nbytes > 0 else None
-    _call('g6d_conv', C.byref(d), _p(x), _p(pc.w), _p(pc.bias), _p(pro_scale), _p(pro_shift), _p(out), _p(ws), _stream(),
-          work=2.0 * B * Do * Ho * Wo * pc.cout * kd * kh * kw * pc.cin)
-    return out
+    if stats is None:       # not fusable here (FFMA path, groups smaller than an epilogue slice): separate pass over the output
+        stats = instnorm_partial(out, rows_per_group=stats_rows, channels=pc.cout, coff=out_coff)
+    return out, stats
+
+
+def fused_stats_enabled():
+    """G6D_FUSED_STATS=0 computes every InstanceNorm statistic with the separate g6d_instnorm_partial pass (A/B checks)."""
+    return os.environ.get('G6D_FUSED_STATS', '1') != '0'
 
 
 def linear_smallm(x, w, bias, act=ACT_NONE):

@@ -172,9 +172,14 @@ int g6d_debug_umma_shift(float* out, int shift, int mode, g6d_stream_t stream);
 /* debug: host_out8[0] != 0 if a pipeline wait inside g6d_conv_tc timed out (kernel bailed out); syncs */
 int g6d_conv_tc_debug(int* host_out8);
 long long g6d_conv_tc_workspace_bytes(const g6d_conv_desc* desc, int kind);
+/* stats (optional, may be NULL): fused InstanceNorm statistics of the OUTPUT.  [M / stats_rows, Cout, 2] doubles
+ * receive, per group of stats_rows consecutive output rows and channel, (sum y, sum y^2) -- what
+ * g6d_instnorm_partial computes in a separate pass over y; feed them to g6d_instnorm_finalize.  Zeroed by
+ * the call.  Allowed when g6d_conv_tc_stats_supported (groups made of whole 32-row slices / image planes). */
+int g6d_conv_tc_stats_supported(const g6d_conv_desc* desc, int kind, long long stats_rows);
 int g6d_conv_tc(const g6d_conv_desc* desc, const float* x, const void* w_hi, const void* w_lo, int w_rows, int kind,
                 const float* bias, const float* pro_scale, const float* pro_shift, float* y, void* ws,
-                g6d_stream_t stream);
+                double* stats, long long stats_rows, g6d_stream_t stream);
 /* [Cout, Cin, taps] (reference layout) -> hi/lo [rows_pad, taps*Cin_pad] of the given kind; optional BN-fold scale */
 int g6d_pack_conv_weight_tc(const float* w, void* out_hi, void* out_lo, int Cout, int Cin, int Cin_pad, int taps,
                             int rows_pad, const float* cout_scale, int kind, g6d_stream_t stream);

@@ -162,3 +162,30 @@ def test_tc_f16_saturates_instead_of_overflowing(ops, kind):
     assert torch.isfinite(y).all()
     if kind == 'tf32':
         assert rel_err(nchw(y), torch.full((1, 32, 8, 8), 64e3)) < 1e-5
+
+
+@pytest.mark.parametrize('case', ['flat2d', 'strided3d', 'splitk', 'onexone'])
+def test_tc_fused_output_statistics(ops, case):
+    """The InstanceNorm moments a convolution's epilogue (or its split-K reduce) accumulates equal the
+    separate pass over its output (g6d_instnorm_partial), and the resulting scale / shift match torch."""
+    if case == 'flat2d':
+        x = torch.randn(3, 64, 16, 16, generator=g(50)); w = torch.randn(64, 64, 3, 3, generator=g(51)) * 0.05; stride, rows = 1, 256
+    elif case == 'strided3d':
+        x = torch.randn(2, 64, 8, 8, 8, generator=g(52)); w = torch.randn(128, 64, 3, 3, 3, generator=g(53)) * 0.03; stride, rows = 2, 64
+    elif case == 'splitk':
+        x = torch.randn(2, 512, 4, 4, 4, generator=g(54)); w = torch.randn(512, 512, 3, 3, 3, generator=g(55)) * 0.01; stride, rows = 1, 64
+    else:
+        x = torch.randn(20, 768, 4, 4, generator=g(56)); w = torch.randn(512, 768, 1, 1, generator=g(57)) * 0.03; stride, rows = 1, 320
+    b = torch.randn(w.shape[0], generator=g(58))
+    pc = ops.pack_conv(w.cuda(), b.cuda(), stride=stride, pad=1 if w.shape[-1] == 3 else 0)
+    y, ws = ops.conv(nhwc(x), pc, stats_rows=rows)
+    want = ops.instnorm_partial(y, rows_per_group=rows)
+    assert ws.shape == want.shape
+    np.testing.assert_allclose(ws.cpu().numpy(), want.cpu().numpy(), rtol=2e-6, atol=1e-4)
+    ps, pb = ops.instnorm_finalize(ws, rows, 1e-5)
+    conv = F.conv3d if x.dim() == 5 else F.conv2d
+    ref = conv(x.double(), w.double(), b.double(), stride=stride, padding=1 if w.shape[-1] == 3 else 0)
+    flat = ref.flatten(2).transpose(1, 2).reshape(-1, rows, w.shape[0])          # [groups, rows, C] (groups of whole samples)
+    mean, var = flat.mean(1), flat.var(1, unbiased=False)
+    np.testing.assert_allclose(ps.cpu().numpy(), (1 / torch.sqrt(var + 1e-5)).float().numpy(), rtol=2e-5)
+    np.testing.assert_allclose(pb.cpu().numpy(), (-mean / torch.sqrt(var + 1e-5)).float().numpy(), rtol=1e-4, atol=2e-5)
