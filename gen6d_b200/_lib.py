@@ -51,6 +51,7 @@ _SIGNATURES = {
     'g6d_instnorm_finalize': [P, L, I, L, F, P, P, P],
     'g6d_conv': [C.POINTER(ConvDesc), P, P, P, P, P, P, P, P],
     'g6d_conv_workspace_bytes': [C.POINTER(ConvDesc)],
+    'g6d_vgg_first_block': [P, P, P, P, I, I, I, P],
     'g6d_pack_conv_weight': [P, P, I, I, I, I, P, P],
     'g6d_conv_tc_supported': [C.POINTER(ConvDesc), I],
     'g6d_conv_tc_debug': [C.POINTER(C.c_int)],
@@ -68,7 +69,7 @@ _SIGNATURES = {
     'g6d_sel_ref_sums': [P, I, I, I, P, P, P],
     'g6d_sel_corr_prologue': [P, P, P, I, I, I, F, P, P, P],
     'g6d_sel_corr_score': [P, P, I, I, I, P, P],
-    'g6d_sel_corr_score3': [P, P, P, P, P, P, I, I, I, I, I, P, P, P],
+    'g6d_sel_corr_score3': [P, P, P, P, P, P, I, I, I, I, I, P, P, P, P],
     'g6d_sel_corr_score3_workspace_bytes': [I, I, I, I],
     'g6d_sel_vp_norm': [P, I, I, F, P, I, I, P],
     'g6d_sel_max_angle_add': [P, P, P, I, I, I, P],

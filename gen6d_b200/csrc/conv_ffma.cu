@@ -264,6 +264,81 @@ __global__ void __launch_bounds__(128) conv3x3_c4_o64_kernel(const float* __rest
     }
 }
 
+// The same layer FUSED with the ReLU and the 2x2 max-pool that follow it in VGG (pretrain_models.py:
+// features[0:4]; nothing on the path reads the full-resolution 64-channel map): a thread owns 16 output
+// channels of one POOLED pixel (a quad of lanes = 64 channels = one 256-byte output row), keeps the
+// 4x4 input window in registers and applies each tap's weights to the four conv outputs under the pool.
+// Writes 1/4 of the bytes and saves the pool's read + write: the unfused pair moves 78.6 + 78.6 + 19.7 MB
+// per 480x640 frame, this kernel 4.9 + 19.7 MB.  Accumulation order per output equals the unfused
+// kernel's (taps ky-major, channels innermost-first; channel 3 is the zero padding), so the result is
+// bit-identical to conv -> ReLU -> maxpool.
+__global__ void __launch_bounds__(128) conv3x3_c4_o64_relu_pool_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                                       const float* __restrict__ bias, float* __restrict__ y,
+                                                                       int B, int H, int W) {
+    __shared__ __align__(16) float ws[36 * 64];
+    __shared__ float bs[64];
+    for (int i = threadIdx.x; i < 36 * 64; i += blockDim.x) ws[i] = w[i];
+    if (threadIdx.x < 64) bs[threadIdx.x] = bias ? bias[threadIdx.x] : 0.f;
+    __syncthreads();
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int q = (int)(t & 3);                       // channels [16 q, 16 q + 16)
+    const long long pp = t >> 2;                      // pooled pixel
+    const int Hp = H >> 1, Wp = W >> 1;
+    if (pp >= (long long)B * Hp * Wp) return;
+    const int xp = (int)(pp % Wp), yp = (int)((pp / Wp) % Hp);
+    const long long b = pp / ((long long)Wp * Hp);
+    // 4x4 input window rows 2yp-1 .. 2yp+2, columns 2xp-1 .. 2xp+2 (zero outside the image)
+    float3 win[4][4];
+#pragma unroll
+    for (int dy = 0; dy < 4; ++dy) {
+        const int yi = 2 * yp - 1 + dy;
+#pragma unroll
+        for (int dx = 0; dx < 4; ++dx) {
+            const int xi = 2 * xp - 1 + dx;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if ((unsigned)yi < (unsigned)H && (unsigned)xi < (unsigned)W)
+                v = __ldg(reinterpret_cast<const float4*>(x + ((b * H + yi) * W + xi) * 4));
+            win[dy][dx] = make_float3(v.x, v.y, v.z);
+        }
+    }
+    float acc[4][16];
+#pragma unroll
+    for (int o = 0; o < 16; ++o) { const float bv = bs[q * 16 + o]; acc[0][o] = bv; acc[1][o] = bv; acc[2][o] = bv; acc[3][o] = bv; }
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky) {
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx) {
+            const float* wr = ws + (ky * 3 + kx) * 4 * 64 + q * 16;
+#pragma unroll
+            for (int o4 = 0; o4 < 4; ++o4) {
+                const float4 w0 = *reinterpret_cast<const float4*>(wr + o4 * 4);
+                const float4 w1 = *reinterpret_cast<const float4*>(wr + 64 + o4 * 4);
+                const float4 w2 = *reinterpret_cast<const float4*>(wr + 128 + o4 * 4);
+#pragma unroll
+                for (int px = 0; px < 4; ++px) {                       // the four conv outputs under the pool
+                    const float3 v = win[(px >> 1) + ky][(px & 1) + kx];
+                    float* a = acc[px] + o4 * 4;
+                    a[0] = fmaf(v.x, w0.x, fmaf(v.y, w1.x, fmaf(v.z, w2.x, a[0])));
+                    a[1] = fmaf(v.x, w0.y, fmaf(v.y, w1.y, fmaf(v.z, w2.y, a[1])));
+                    a[2] = fmaf(v.x, w0.z, fmaf(v.y, w1.z, fmaf(v.z, w2.z, a[2])));
+                    a[3] = fmaf(v.x, w0.w, fmaf(v.y, w1.w, fmaf(v.z, w2.w, a[3])));
+                }
+            }
+        }
+    }
+    float4* yr = reinterpret_cast<float4*>(y + pp * 64 + q * 16);
+#pragma unroll
+    for (int o4 = 0; o4 < 4; ++o4) {
+        float r[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const int o = o4 * 4 + e;
+            r[e] = fmaxf(fmaxf(fmaxf(acc[0][o], acc[1][o]), fmaxf(acc[2][o], acc[3][o])), 0.f);     // max-pool of the ReLUs
+        }
+        __stcs(yr + o4, make_float4(r[0], r[1], r[2], r[3]));
+    }
+}
+
 static int fill_params(const g6d_conv_desc* d, ConvP& p) {
     G6D_REQUIRE(d != nullptr, "g6d_conv: null desc");
     G6D_REQUIRE(d->B > 0 && d->D > 0 && d->H > 0 && d->W > 0 && d->Cin > 0 && d->Cout > 0, "g6d_conv: bad dims");
@@ -342,6 +417,15 @@ extern "C" int g6d_conv(const g6d_conv_desc* desc, const float* x, const float* 
                                                                      p.act);
         G6D_CHECK_LAUNCH("g6d_conv(splitk reduce)");
     }
+    return G6D_OK;
+}
+
+extern "C" int g6d_vgg_first_block(const float* x, const float* w, const float* bias, float* y, int B, int H, int W,
+                                   g6d_stream_t stream) {
+    G6D_REQUIRE(x && w && y && B > 0 && H >= 2 && W >= 2 && (H & 1) == 0 && (W & 1) == 0, "g6d_vgg_first_block: bad args (H, W even)");
+    const long long threads = (long long)B * (H / 2) * (W / 2) * 4;
+    conv3x3_c4_o64_relu_pool_kernel<<<ceil_div(threads, 128), 128, 0, as_stream(stream)>>>(x, w, bias, y, B, H, W);
+    G6D_CHECK_LAUNCH("g6d_vgg_first_block");
     return G6D_OK;
 }
 

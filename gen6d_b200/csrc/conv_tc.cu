@@ -63,6 +63,17 @@ template <> struct KindCfg<G6D_TC_F16> {
     static constexpr float CROSS = 1.f / 2048.f;
 };
 constexpr float F16_LO_SCALE = 2048.f;
+// K order inside a 64-element fp16 K-block.  A producer thread fills one 16-byte shared-memory chunk
+// (8 halves) of a tile row from two 128-bit global loads; to keep BOTH loads of a warp fully coalesced
+// (8 lanes x 16 B = one 128-byte line per row) lane c reads channels [4c, 4c+4) and [32+4c, 32+4c+4), so
+// chunk c holds those eight channels.  The contraction does not care about the order of K as long as the
+// weight operand uses the same one: the pack / split kernels write K position p from source channel
+// f16_k_source(p).  (ncu, round 2: with adjacent channels per lane every gather touched 8 lines per
+// instruction instead of 4 -- twice the L1 tag requests and L2 sectors of the ideal.)
+__host__ __device__ __forceinline__ int f16_k_source(int p) {      // p in [0, 64)
+    const int c = p >> 3, i = p & 7;
+    return i < 4 ? 4 * c + i : 32 + 4 * c + (i - 4);
+}
 
 struct ConvTcP {
     const float* x; const float* bias; const float* ps; const float* pb;
@@ -272,7 +283,7 @@ conv_tc2_kernel(const ConvTcP p, const Tc2Work wk, const __grid_constant__ CUten
         // =============================== A producers ===============================
         // All 8 warps fill every K-block: 4 rows x one 16-byte smem chunk (4 or 8 channels) per thread.
         const int chunk = threadIdx.x & 7;
-        const int cofs = chunk * 4 * NV;                   // this thread's first channel inside the K-block
+        const int cofs = chunk * 4;                        // this thread's channels inside the K-block: [cofs, cofs+4) (+32 for the 2nd load)
         const int r0 = threadIdx.x >> 3;                   // rows r0 + 32*j, j = 0..3
         int git = 0;                                       // global K-block counter of this CTA
         for (int w = blockIdx.x; w < wk.total; w += gridDim.x) {
@@ -322,7 +333,7 @@ conv_tc2_kernel(const ConvTcP p, const Tc2Work wk, const __grid_constant__ CUten
                     if (inb) {
                         const float4* src = reinterpret_cast<const float4*>(xb + ((long long)rb[j] * plane_sz + rsp[j] + tap_sp) * p.ics);
 #pragma unroll
-                        for (int e = 0; e < NV; ++e) v[q][j][e] = __ldg(src + e);
+                        for (int e = 0; e < NV; ++e) v[q][j][e] = __ldg(src + e * 8);
                         okm[q] |= 1u << j;
                     }
                 }
@@ -348,7 +359,7 @@ conv_tc2_kernel(const ConvTcP p, const Tc2Work wk, const __grid_constant__ CUten
                                 shp = reinterpret_cast<const float4*>(p.pb + g * p.Cin + kc[q]);
                             }
 #pragma unroll
-                            for (int e = 0; e < NV; ++e) v[q][j][e] = affine4(v[q][j][e], __ldg(scp + e), __ldg(shp + e), relu);
+                            for (int e = 0; e < NV; ++e) v[q][j][e] = affine4(v[q][j][e], __ldg(scp + e * 8), __ldg(shp + e * 8), relu);
                         }
                     }
                 }
@@ -521,30 +532,63 @@ conv_tc2_kernel(const ConvTcP p, const Tc2Work wk, const __grid_constant__ CUten
     }
 }
 
-// Split-K epilogue: y = act(sum_s ws[s] + bias), and (optionally) the fused InstanceNorm statistics of y.
-// Block = 32 consecutive output rows (one group: stats_rows % 32 == 0), thread = channel (strided).
-__global__ void __launch_bounds__(256) conv_tc_reduce_kernel(const float* __restrict__ ws, const float* __restrict__ bias,
-                                                             float* __restrict__ y, int M, int Cout, int splits, int ocs, int oco,
-                                                             int act, double* __restrict__ stats, long long stats_rows) {
-    const int m0 = blockIdx.x * 32;
-    const int m1 = min(M, m0 + 32);
+// Split-K epilogue: y = act(sum_s ws[s] + bias); one thread per output element.
+__global__ void conv_tc_reduce_kernel(const float* __restrict__ ws, const float* __restrict__ bias,
+                                      float* __restrict__ y, int M, int Cout, int splits, int ocs, int oco, int act) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (long long)M * Cout) return;
+    const int n = (int)(i % Cout);
+    const long long m = i / Cout;
+    float v = 0.f;
+    for (int s = 0; s < splits; ++s) v += ws[(long long)s * M * Cout + i];
+    if (bias) v += bias[n];
+    y[m * ocs + oco + n] = tc_act(v, act);
+}
+
+// The same with the fused InstanceNorm statistics of y: a 256-thread block owns 32 consecutive output
+// rows (one group: stats_rows % 32 == 0) x 64 channels; thread = (channel, 8-row slice); the four slices
+// are combined in shared memory and one (sum, sum^2) pair per (block, channel) goes to the fp64 accumulators.
+__global__ void __launch_bounds__(256) conv_tc_reduce_stats_kernel(const float* __restrict__ ws, const float* __restrict__ bias,
+                                                                   float* __restrict__ y, int M, int Cout, int splits, int ocs,
+                                                                   int oco, int act, double* __restrict__ stats, long long stats_rows) {
+    __shared__ float red[2][4][64];
+    const int c = threadIdx.x & 63, rg = threadIdx.x >> 6;
+    const int n = blockIdx.y * 64 + c;
+    const int m0 = blockIdx.x * 32 + rg * 8;
     const long long slab = (long long)M * Cout;
-    for (int n = threadIdx.x; n < Cout; n += blockDim.x) {
+    float s1 = 0.f, s2 = 0.f;
+    if (n < Cout) {
         const float b = bias ? bias[n] : 0.f;
-        float s1 = 0.f, s2 = 0.f;
-        for (int m = m0; m < m1; ++m) {
-            const long long i = (long long)m * Cout + n;
-            float v = 0.f;
-            for (int s = 0; s < splits; ++s) v += ws[(long long)s * slab + i];
-            v = tc_act(v + b, act);
-            y[(long long)m * ocs + oco + n] = v;
-            s1 += v; s2 = fmaf(v, v, s2);
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+            const int m = m0 + r;
+            if (m < M) {
+                const long long i = (long long)m * Cout + n;
+                float v = 0.f;
+                for (int s = 0; s < splits; ++s) v += ws[(long long)s * slab + i];
+                v = tc_act(v + b, act);
+                y[(long long)m * ocs + oco + n] = v;
+                s1 += v; s2 = fmaf(v, v, s2);
+            }
         }
-        if (stats) {
-            double* dst = stats + ((long long)(m0 / stats_rows) * Cout + n) * 2;
-            atomicAdd(dst, (double)s1);
-            atomicAdd(dst + 1, (double)s2);
-        }
+    }
+    red[0][rg][c] = s1; red[1][rg][c] = s2;
+    __syncthreads();
+    if (threadIdx.x < 128) {
+        const int q = threadIdx.x >> 6;                       // 0: sum, 1: sum of squares
+        const float t = red[q][0][c] + red[q][1][c] + red[q][2][c] + red[q][3][c];
+        if (n < Cout) atomicAdd(stats + ((long long)((blockIdx.x * 32) / stats_rows) * Cout + n) * 2 + q, (double)t);
+    }
+}
+
+static void launch_reduce(const float* ws, const float* bias, float* y, int M, int Cout, int splits, int ocs, int oco, int act,
+                          double* stats, long long stats_rows, cudaStream_t st) {
+    if (stats) {
+        dim3 grid(ceil_div(M, 32), ceil_div(Cout, 64));
+        conv_tc_reduce_stats_kernel<<<grid, 256, 0, st>>>(ws, bias, y, M, Cout, splits, ocs, oco, act, stats, stats_rows);
+    } else {
+        const long long n = (long long)M * Cout;
+        conv_tc_reduce_kernel<<<ceil_div(n, 256), 256, 0, st>>>(ws, bias, y, M, Cout, splits, ocs, oco, act);
     }
 }
 
@@ -679,10 +723,11 @@ __device__ __forceinline__ void split_f16_scalar(float v, __half& h, __half& l) 
     h = __ushort_as_half((unsigned short)(hh & 0xffffu));
     l = __ushort_as_half((unsigned short)(ll & 0xffffu));
 }
+// rows of K-major operands, K a multiple of 64: position p of every 64-block comes from source f16_k_source(p)
 __global__ void split_f16_kernel(const float* __restrict__ in, __half* __restrict__ hi, __half* __restrict__ lo, long long n) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    split_f16_scalar(in[i], hi[i], lo[i]);
+    split_f16_scalar(in[(i & ~63ll) + f16_k_source((int)(i & 63))], hi[i], lo[i]);
 }
 
 // [Cout, Cin, taps] (reference layout) -> hi/lo [rows_pad, taps*Cin_pad], K index = tap*Cin_pad + c
@@ -695,7 +740,9 @@ __global__ void pack_conv_weight_tc_kernel(const float* __restrict__ w, void* __
     if (i >= K * rows_pad) return;
     const int o = (int)(i / K);
     const long long k = i % K;
-    const int tap = (int)(k / Cin_pad), c = (int)(k % Cin_pad);
+    const int tap = (int)(k / Cin_pad);
+    int c = (int)(k % Cin_pad);
+    if constexpr (KIND == G6D_TC_F16) c = (c & ~63) + f16_k_source(c & 63);       // K order of the fp16 K-block
     float v = 0.f;
     if (o < Cout && c < Cin) {
         v = w[((long long)o * Cin + c) * taps + tap];
@@ -810,7 +857,7 @@ conv_tcflat_kernel(const ConvFlatP p, const __grid_constant__ CUtensorMap map_hi
     if (warp < TC_PRODUCER_WARPS) {
         // =============================== A producers ===============================
         const int chunk = threadIdx.x & 7;
-        const int cofs = chunk * 4 * NV;
+        const int cofs = chunk * 4;                             // channels [cofs, cofs+4) (+32 for the 2nd load), see f16_k_source
         const int r0 = threadIdx.x >> 3;                        // rows r0 + 32*j
         const long long plane = (long long)p.H * p.W;
         const long long gi = (long long)b / p.group_rows;
@@ -839,7 +886,7 @@ conv_tcflat_kernel(const ConvFlatP p, const __grid_constant__ CUtensorMap map_hi
                     if (off[j] >= 0) {
                         const float4* src = reinterpret_cast<const float4*>(xplane + (long long)off[j] * p.ics);
 #pragma unroll
-                        for (int e = 0; e < NV; ++e) v[j][e] = __ldg(src + e);
+                        for (int e = 0; e < NV; ++e) v[j][e] = __ldg(src + e * 8);
                     }
                 }
 #pragma unroll
@@ -857,7 +904,7 @@ conv_tcflat_kernel(const ConvFlatP p, const __grid_constant__ CUtensorMap map_hi
                             shp = reinterpret_cast<const float4*>(p.pb + gi * p.Cin + c);
                         }
 #pragma unroll
-                        for (int e = 0; e < NV; ++e) v[j][e] = affine4(v[j][e], __ldg(scp + e), __ldg(shp + e), relu);
+                        for (int e = 0; e < NV; ++e) v[j][e] = affine4(v[j][e], __ldg(scp + e * 8), __ldg(shp + e * 8), relu);
                     }
                     const uint32_t so = r * 128 + ((chunk ^ (r & 7)) << 4);
                     split_store<KIND>(a_hi(s) + so, a_lo(s) + so, v[j]);
@@ -1164,8 +1211,7 @@ extern "C" int g6d_conv_tc(const g6d_conv_desc* desc, const float* x, const void
             if (fp.splits > 1) {
                 const long long n = (long long)fp.M * fp.Cout;
                 (void)n;
-                conv_tc_reduce_kernel<<<ceil_div(fp.M, 32), fp.Cout >= 256 ? 256 : (fp.Cout >= 128 ? 128 : 64), 0, st>>>(
-                    fp.ws, bias, y, fp.M, fp.Cout, fp.splits, fp.ocs, fp.oco, fp.act, fp.stats, fp.stats_rows);
+                launch_reduce(fp.ws, bias, y, fp.M, fp.Cout, fp.splits, fp.ocs, fp.oco, fp.act, fp.stats, fp.stats_rows, st);
                 G6D_CHECK_LAUNCH("g6d_conv_tc(flat reduce)");
             }
             return G6D_OK;
@@ -1190,8 +1236,7 @@ extern "C" int g6d_conv_tc(const g6d_conv_desc* desc, const float* x, const void
     if (p.splits > 1) {
         const long long n = (long long)p.M * p.Cout;
         (void)n;
-        conv_tc_reduce_kernel<<<ceil_div(p.M, 32), p.Cout >= 256 ? 256 : (p.Cout >= 128 ? 128 : 64), 0, st>>>(
-            p.ws, bias, y, p.M, p.Cout, p.splits, p.ocs, p.oco, p.act, p.stats, p.stats_rows);
+        launch_reduce(p.ws, bias, y, p.M, p.Cout, p.splits, p.ocs, p.oco, p.act, p.stats, p.stats_rows, st);
         G6D_CHECK_LAUNCH("g6d_conv_tc(splitk reduce)");
     }
     return G6D_OK;
@@ -1200,6 +1245,7 @@ extern "C" int g6d_conv_tc(const g6d_conv_desc* desc, const float* x, const void
 extern "C" int g6d_split_operand(const float* in, void* hi, void* lo, long long n, int kind, g6d_stream_t stream) {
     G6D_REQUIRE(in && hi && lo && n > 0, "g6d_split_operand: bad args");
     G6D_REQUIRE(kind == G6D_TC_TF32 || kind == G6D_TC_F16, "g6d_split_operand: bad operand kind %d", kind);
+    G6D_REQUIRE(kind != G6D_TC_F16 || (n & 63) == 0, "g6d_split_operand: fp16 operands are laid out in 64-element K-blocks (n = %lld)", n);
     if (kind == G6D_TC_F16)
         split_f16_kernel<<<ceil_div(n, 256), 256, 0, as_stream(stream)>>>(in, static_cast<__half*>(hi), static_cast<__half*>(lo), n);
     else

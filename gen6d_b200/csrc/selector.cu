@@ -160,6 +160,7 @@ __global__ void __launch_bounds__(256, 6) sel_corr_dots_kernel(const ScoreLevels
             if (lane == 0) last = atomicAdd(done + item, (int)(next - r)) + (int)(next - r) == P;
             last = __shfl_sync(0xffffffffu, last, 0);
             if (last) {                                                   // warp-uniform
+                if (lane == 0) done[item] = 0;                            // leave the counters zero for the next call
                 __threadfence();                                          // acquire: the other CTAs' t values
                 const float* tp = t_out + first;
                 float m = -INFINITY;
@@ -263,6 +264,11 @@ __global__ void sel_vp_norm_kernel(const float* __restrict__ score, int n, float
     const float rstd = (float)(1.0 / sqrt(var + (double)eps));
     const float fm = (float)mean;
     for (int i = threadIdx.x; i < n; i += blockDim.x) feats[(long long)i * cstride + coff + l] = (s[i] - fm) * rstd;
+    // the channels between the last score and the row end are padding the consumer multiplies by zero
+    // weights: they must be finite, so the first block clears them (no separate fill pass over feats)
+    if (l == 0)
+        for (int c = coff + (int)gridDim.x; c < cstride; ++c)
+            for (int i = threadIdx.x; i < n; i += blockDim.x) feats[(long long)i * cstride + c] = 0.f;
 }
 
 __global__ void sel_max_angle_add_kernel(const float* __restrict__ x, const float* __restrict__ embed,
@@ -368,12 +374,12 @@ extern "C" int g6d_sel_corr_score(const float* ref, const float* q, int S, int P
 extern "C" long long g6d_sel_corr_score3_workspace_bytes(int S, int P0, int P1, int P2) {
     if (S <= 0 || P0 <= 0 || P1 <= 0 || P2 <= 0) { set_error("g6d_sel_corr_score3_workspace_bytes: bad args"); return -1; }
     const long long rows = (long long)S * ((long long)P0 + P1 + P2);
-    return ((rows + 3) / 4) * 4 * (long long)sizeof(float) + 3ll * S * (long long)sizeof(int);
+    return ((rows + 3) / 4) * 4 * (long long)sizeof(float);
 }
 
 extern "C" int g6d_sel_corr_score3(const float* ref0, const float* ref1, const float* ref2, const float* q0,
                                    const float* q1, const float* q2, int S, int P0, int P1, int P2, int C, float* score,
-                                   float* ws, g6d_stream_t stream) {
+                                   float* ws, int* counters, g6d_stream_t stream) {
     G6D_REQUIRE(ref0 && ref1 && ref2 && q0 && q1 && q2 && score && ws && S > 0 && P0 > 0 && P1 > 0 && P2 > 0,
                 "g6d_sel_corr_score3: bad args");
     G6D_REQUIRE(C == 512, "g6d_sel_corr_score3: C must be 512 (got %d)", C);
@@ -397,11 +403,8 @@ extern "C" int g6d_sel_corr_score3(const float* ref0, const float* ref1, const f
     long long grid = (pairs + 7) / 8;                    // 8 warps per CTA, one row pair per warp per trip
     const long long full = (long long)occ[fused] * kNumSMs;
     if (grid > full) grid = full;
-    // workspace: [rows] floats of per-location inner products, then 3*S completion counters
-    int* done = reinterpret_cast<int*>(ws + ((L.row_end[2] + 3) / 4) * 4);
-    if (fused) {
-        cudaError_t e = cudaMemsetAsync(done, 0, sizeof(int) * 3 * S, st);
-        if (e != cudaSuccess) { set_error("g6d_sel_corr_score3: memset: %s", cudaGetErrorString(e)); return G6D_ECUDA; }
+    if (fused && counters) {
+        int* done = counters;
         long long chunk = (L.row_end[2] + grid - 1) / grid;
         chunk += chunk & 1;                                  // even: row pairs never straddle two CTAs
         grid = (L.row_end[2] + chunk - 1) / chunk;

@@ -18,13 +18,17 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
+// try_wait with a suspend-time hint: the thread sleeps inside the instruction until the phase completes
+// (or the hint expires) instead of re-polling.  ncu on the round-2 kernel: the un-hinted polls of the
+// waiting roles (MMA issuer, TMA and epilogue warps) were 5.7 M SYNCS + 4.5 M bail-out flag reads per
+// launch, ~15 % of the L1 / shared-memory data-pipe wavefronts the operand feed competes for.
 __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
     uint32_t ok;
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
         "selp.b32 %0, 1, 0, p;\n\t}"
-        : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+        : "=r"(ok) : "r"(bar), "r"(parity), "r"(0x989680u) : "memory");
     return ok != 0;
 }
 // Bounded wait: a protocol bug must never hang the GPU.  On timeout (~0.25 s) the waiter records
@@ -35,7 +39,9 @@ static __device__ int g_tc_timeout[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int who = 0, int iter = 0) {
     if (mbar_try_wait(bar, parity)) return;
     const long long t0 = clock64();
+    unsigned spins = 0;
     while (!mbar_try_wait(bar, parity)) {
+        if ((++spins & 63u) != 0) continue;                 // the bail-out flag is global memory: look at it rarely
         if (*(volatile int*)&g_tc_timeout[0] != 0) return;
         if (clock64() - t0 > 500000000ll) {
             if (atomicCAS(&g_tc_timeout[0], 0, 1) == 0) {

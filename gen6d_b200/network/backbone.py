@@ -28,12 +28,19 @@ def pack_vgg(params):
     return packed
 
 
-def vgg_pyramid(packed, x):
+def vgg_pyramid(packed, x, full_res=False):
     """x: [N, H, W, 4] ImageNet-normalised, channel 3 zero.  Returns the six maps
-    [1/1, 1/2, 1/4, 1/8, 1/16 (pre-ReLU), 1/32 (max-pool of the pre-ReLU map)], channels-last."""
+    [1/1 (None unless full_res), 1/2, 1/4, 1/8, 1/16 (pre-ReLU), 1/32 (max-pool of the pre-ReLU map)],
+    channels-last.  Nothing on the inference path reads the 1/1 map, so the first conv, its ReLU and the
+    first max-pool run as one kernel (g6d_vgg_first_block) that never writes it."""
     outs = []
+    fused = not full_res and x.shape[1] % 2 == 0 and x.shape[2] % 2 == 0 and x.shape[3] == 4
     for bi, block in enumerate(VGG11_BLOCKS):
-        if bi > 0:
+        if bi == 0 and fused:
+            outs.append(None)
+            x = ops.vgg_first_block(x, packed[block[0]])
+            continue
+        if bi > 0 and not (bi == 1 and fused):
             x = ops.maxpool2x2(x)
         for slot in block:
             x = ops.conv(x, packed[slot], act=ops.ACT_NONE if slot == 25 else ops.ACT_RELU)

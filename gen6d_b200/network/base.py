@@ -63,6 +63,7 @@ class PackedModule(nn.Module):
         other = copy.copy(self)
         other.stages = StageCache()
         other._pinned, other._pinned_next = {}, {}
+        other.__dict__.pop('_s2_done', None)         # per-handle scratch (selector): never shared between streams
         return other
 
     def _to_dev(self, array, dtype=None):

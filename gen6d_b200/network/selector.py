@@ -135,6 +135,16 @@ class ViewpointSelector(PackedModule):
         self.ref_pose_embed = x.reshape(rfn, 512)
         self.bump_generation()          # captured graphs / worker clones hold pointers to the previous reference set
 
+    def _s2_counters(self):
+        """Completion counters of the fused S2 kernel: zero between calls (the kernel restores that), private
+        to this handle (worker clones run concurrently on other streams and get their own)."""
+        n = 3 * self.ref_shape[0] * self.ref_shape[1]
+        c = self.__dict__.get('_s2_done')
+        if c is None or c.numel() != n or c.device != self.device:
+            c = torch.zeros(n, device=self.device, dtype=torch.int32)
+            self.__dict__['_s2_done'] = c
+        return c
+
     def _finalize(self, ws, rows_total):
         """InstanceNorm scale / shift from the (sum, sum-of-squares) moments a convolution's epilogue
         produced (fp64).  The group may span GPUs: the moments are all-reduced first, so the statistics are
@@ -167,9 +177,9 @@ class ViewpointSelector(PackedModule):
         S_total = self.rfn_total * an
         dev = self.device
         cat_buf = torch.empty(S, 4, 4, 768, device=dev, dtype=torch.float32)
-        feats = torch.zeros(S, FEAT_PAD, device=dev, dtype=torch.float32)
+        feats = torch.empty(S, FEAT_PAD, device=dev, dtype=torch.float32)      # cols 0-511: cf3, 512-514 + pad: vp_norm
         scores = ops.sel_corr_score3([r.reshape(S, -1, r.shape[-1]) for r in self.ref_feats_cache],
-                                     [q.reshape(-1, q.shape[-1]) for q in q_feats])
+                                     [q.reshape(-1, q.shape[-1]) for q in q_feats], counters=self._s2_counters())
         br = Branches(3 if self.comm.world == 1 else 1)     # the three towers only meet in cat_buf
         keep = []
 
@@ -192,10 +202,10 @@ class ViewpointSelector(PackedModule):
             ops.sel_vp_norm(scores, feats, 512, IN_EPS)                 # vp_norm, selector.py:201
         else:   # InstanceNorm2d over ALL (rfn, an): gather the 3*S_total scores, normalise, keep our rows
             all_scores = self.comm.all_gather_cat(scores, dim=1).contiguous()
-            tmp = torch.zeros(S_total, 4, device=dev, dtype=torch.float32)
+            tmp = torch.empty(S_total, 4, device=dev, dtype=torch.float32)
             ops.sel_vp_norm(all_scores, tmp, 0, IN_EPS)
             r0, _ = self.comm.shard_range(self.rfn_total)
-            feats[:, 512:515] = tmp[r0 * an:r0 * an + S, :3]
+            feats[:, 512:516] = tmp[r0 * an:r0 * an + S]
         x = ops.conv(feats.reshape(S, 1, 1, FEAT_PAD), p['sp0'], act=ops.ACT_RELU)
         x = ops.conv(x, p['sp2']).reshape(rfn, an, 512)
         sf = ops.sel_max_angle_add(x, self.ref_pose_embed)              # selector.py:203-204

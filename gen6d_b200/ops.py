@@ -360,6 +360,14 @@ def fused_stats_enabled():
     return os.environ.get('G6D_FUSED_STATS', '1') != '0'
 
 
+def vgg_first_block(x, pc):
+    """x [B,H,W,4] -> [B,H/2,W/2,64]: first VGG conv (BN folded) + ReLU + 2x2 max-pool in one kernel."""
+    B, H, W, _ = x.shape
+    out = torch.empty(B, H // 2, W // 2, 64, device=x.device, dtype=torch.float32)
+    _call('g6d_vgg_first_block', _p(x), _p(pc.w), _p(pc.bias), _p(out), B, H, W, _stream())
+    return out
+
+
 def linear_smallm(x, w, bias, act=ACT_NONE):
     """x [M<=8, K], w [N, K] (row-major) -> [M, N]."""
     M, K = x.shape
@@ -434,14 +442,15 @@ def sel_corr_score(ref, q, out=None):
     return out
 
 
-def sel_corr_score3(refs, qs):
-    """refs: 3 x [S, P_l, C]; qs: 3 x [P_l, C] -> score [3, S] in one streaming pass."""
+def sel_corr_score3(refs, qs, counters=None):
+    """refs: 3 x [S, P_l, C]; qs: 3 x [P_l, C] -> score [3, S] in one streaming pass.
+    counters: int32 [3*S], zero (the kernel leaves it zero): one launch; None: dots + finish kernels."""
     S, Cc = refs[0].shape[0], refs[0].shape[2]
     Ps = [r.shape[1] for r in refs]
     out = torch.empty(3, S, device=refs[0].device, dtype=torch.float32)
     ws = torch.empty(_lib.lib().g6d_sel_corr_score3_workspace_bytes(S, *Ps) // 4, device=refs[0].device, dtype=torch.float32)
     _call('g6d_sel_corr_score3', _p(refs[0]), _p(refs[1]), _p(refs[2]), _p(qs[0]), _p(qs[1]), _p(qs[2]), S, Ps[0], Ps[1],
-          Ps[2], Cc, _p(out), _p(ws), _stream(), work=4.0 * (S * sum(Ps) * Cc + sum(Ps) * Cc + 3 * S))
+          Ps[2], Cc, _p(out), _p(ws), _p(counters, torch.int32), _stream(), work=4.0 * (S * sum(Ps) * Cc + sum(Ps) * Cc + 3 * S))
     return out
 
 

@@ -148,6 +148,11 @@ typedef struct g6d_conv_desc {
 int g6d_conv(const g6d_conv_desc* desc, const float* x, const float* w, const float* bias,
              const float* pro_scale, const float* pro_shift, float* y, void* ws, g6d_stream_t stream);
 long long g6d_conv_workspace_bytes(const g6d_conv_desc* desc);
+/* First VGG block in one kernel: 3x3 conv 4 -> 64 (RGB + zero channel, BN folded) + ReLU + 2x2 max-pool
+ * (network/pretrain_models.py:17-31 features[0:4]); x [B,H,W,4], w packed [36,64] (g6d_pack_conv_weight),
+ * y [B,H/2,W/2,64]; H, W even.  Bit-identical to g6d_conv -> ReLU -> g6d_maxpool2x2. */
+int g6d_vgg_first_block(const float* x, const float* w, const float* bias, float* y, int B, int H, int W,
+                        g6d_stream_t stream);
 /* [Cout, Cin, kd, kh, kw] (reference layout) -> [taps*Cin_pad, ldw] with ldw = Cout rounded up
  * to 4; channels [Cin, Cin_pad) and columns [Cout, ldw) are zero; optional per-Cout scale
  * (eval-mode BatchNorm fold). */
@@ -183,7 +188,10 @@ int g6d_conv_tc(const g6d_conv_desc* desc, const float* x, const void* w_hi, con
 /* [Cout, Cin, taps] (reference layout) -> hi/lo [rows_pad, taps*Cin_pad] of the given kind; optional BN-fold scale */
 int g6d_pack_conv_weight_tc(const float* w, void* out_hi, void* out_lo, int Cout, int Cin, int Cin_pad, int taps,
                             int rows_pad, const float* cout_scale, int kind, g6d_stream_t stream);
-/* elementwise hi/lo split of an fp32 array into the given kind (detector reference features as kernels) */
+/* hi/lo split of a K-major fp32 operand [rows, K] into the given kind (detector reference features as
+ * kernels).  G6D_TC_F16 operands use the kernels' K order inside every 64-element block (position p holds
+ * source element 4*(p/8) + p%8 for p%8 < 4, else 32 + 4*(p/8) + p%8 - 4: it keeps the activation gathers
+ * coalesced); K % 64 == 0.  g6d_pack_conv_weight_tc applies the same order. */
 int g6d_split_operand(const float* in, void* hi, void* lo, long long n, int kind, g6d_stream_t stream);
 /* [rows, K] row-major -> [K, rows] (detector reference features [rfn,k,k,512] -> correlation kernels) */
 int g6d_transpose2d(const float* in, float* out, int rows, int cols, g6d_stream_t stream);
@@ -234,14 +242,16 @@ int g6d_sel_corr_prologue(const float* q, const double* sum1, const double* sum2
 int g6d_sel_corr_score(const float* ref, const float* q, int S, int P, int C, float* score, g6d_stream_t stream);
 /* The same score for the three pyramid levels in one streaming pass (what select_que_imgs uses):
  * score [3, S]; ws: g6d_sel_corr_score3_workspace_bytes(S, P0, P1, P2) bytes (per-location inner
- * products, L2-resident, + one completion counter per (level, slice): the warp that finishes the last
- * location of a slice reduces it, so the whole op is one launch). */
+ * products, L2-resident).  counters: 3*S ints, one per (level, slice), ZERO on entry and left zero on
+ * exit (allocate + clear once, reuse for every call on the same stream): the CTA that completes the last
+ * location of a slice reduces it, so the whole op is one launch.  counters == NULL: two launches. */
 long long g6d_sel_corr_score3_workspace_bytes(int S, int P0, int P1, int P2);
 int g6d_sel_corr_score3(const float* ref0, const float* ref1, const float* ref2, const float* q0, const float* q1,
-                        const float* q2, int S, int P0, int P1, int P2, int C, float* score, float* ws,
+                        const float* q2, int S, int P0, int P1, int P2, int C, float* score, float* ws, int* counters,
                         g6d_stream_t stream);
 /* vp_norm (InstanceNorm2d(3), selector.py:78,201): normalise each of the L score rows [L, n]
  * (biased var, eps) and scatter into feats[n, cstride] at channel coff + l. */
+/* (channels [coff + L, cstride) of every feats row -- padding that the consumer multiplies by zero weights -- are set to 0) */
 int g6d_sel_vp_norm(const float* score, int L, int n, float eps, float* feats, int cstride, int coff,
                     g6d_stream_t stream);
 /* selector.py:203-204: out[r,c] = max_a x[r,a,c] + embed[r,c] */

@@ -148,11 +148,29 @@ def test_sel_corr_score3_matches_per_level(ops):
     S = 10
     refs = [F.normalize(torch.rand(S, P, 512, generator=g(30 + i)), dim=2) for i, P in enumerate((256, 64, 16))]
     qs = [F.normalize(torch.rand(P, 512, generator=g(40 + i)), dim=1) for i, P in enumerate((256, 64, 16))]
-    got = ops.sel_corr_score3([r.cuda() for r in refs], [q.cuda() for q in qs])
+    got = ops.sel_corr_score3([r.cuda() for r in refs], [q.cuda() for q in qs])        # dots + finish launches
     for l in range(3):
         s = torch.einsum('pc,spc->sp', qs[l], refs[l])
         want = torch.sum(s * (s / s.max(1, keepdim=True)[0]), 1)
         close(got[l], want, rtol=1e-5, atol=1e-6)
+    # one launch: the CTA that completes a slice reduces it; the counters come back zero, call after call
+    counters = torch.zeros(3 * S, dtype=torch.int32, device='cuda')
+    for _ in range(3):
+        fused = ops.sel_corr_score3([r.cuda() for r in refs], [q.cuda() for q in qs], counters=counters)
+        assert torch.equal(fused, got)
+        assert int(counters.abs().sum()) == 0
+
+
+@pytest.mark.parametrize('S', [1, 7, 320])
+def test_sel_corr_score3_fused_ragged_sizes(ops, S):
+    """Odd slice counts / location counts that do not divide the per-CTA chunk."""
+    Ps = (25, 9, 4)
+    refs = [torch.rand(S, P, 512, generator=g(60 + i)).cuda() for i, P in enumerate(Ps)]
+    qs = [torch.rand(P, 512, generator=g(70 + i)).cuda() for i, P in enumerate(Ps)]
+    counters = torch.zeros(3 * S, dtype=torch.int32, device='cuda')
+    a = ops.sel_corr_score3(refs, qs)
+    b = ops.sel_corr_score3(refs, qs, counters=counters)
+    assert torch.equal(a, b) and int(counters.abs().sum()) == 0
 
 
 def test_attention_layernorm(ops):
@@ -170,3 +188,22 @@ def test_linear_smallm(ops):
     x = torch.randn(3, 4096, generator=g(25)); w = torch.randn(64, 4096, generator=g(26)) * 0.02
     b = torch.randn(64, generator=g(27))
     close(ops.linear_smallm(x.cuda(), w.cuda(), b.cuda(), act=ops.ACT_LEAKY01), F.leaky_relu(F.linear(x, w, b), 0.1))
+
+
+@pytest.mark.parametrize('B,H,W', [(1, 64, 96), (3, 18, 22), (2, 128, 128)])
+def test_vgg_first_block_fused_equals_conv_relu_pool(ops, B, H, W):
+    """g6d_vgg_first_block (3x3 conv 4->64 + ReLU + 2x2 max-pool in one kernel) is bit-identical to the
+    three separate kernels and matches torch."""
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(B, 3, H, W, generator=g)
+    w = torch.randn(64, 3, 3, 3, generator=g) * 0.2
+    b = torch.randn(64, generator=g) * 0.1
+    x4 = torch.zeros(B, H, W, 4)
+    x4[..., :3] = x.permute(0, 2, 3, 1)
+    x4 = x4.cuda()
+    pc = ops.pack_conv(w.cuda(), b.cuda(), pad=1)
+    fused = ops.vgg_first_block(x4, pc)
+    sep = ops.maxpool2x2(ops.conv(x4, pc, act=ops.ACT_RELU))
+    assert torch.equal(fused, sep)
+    want = F.max_pool2d(F.relu(F.conv2d(x, w, b, padding=1)), 2).permute(0, 2, 3, 1)
+    np.testing.assert_allclose(fused.cpu().numpy(), want.numpy(), atol=2e-5)
