@@ -469,6 +469,8 @@ def run_ours(args, rank, world, local_rank):
                       + ('fp16 hi + 2^11-scaled fp16 lo halves, kind::f16' if f16 else 'tf32 hi/lo halves, kind::tf32') + ')',
             'bound': 'tensor', 'achieved': conv['work'] / max(conv['ms'], 1e-9) / 1e9, 'peak': peaks['bf16_tflops'], 'unit': 'TFLOP/s',
             'traffic': traffic.get('conv'),
+            'traffic_of': 'DRAM bytes of ONE launch of the 3x3 512->512 layer on a 120x160 map (tools/conv_one.py, ncu --set full): '
+                          'its 4.2 GB of operand reads are served from L2; activations + weights come from HBM once',
             'peak_source': f"{peaks['src']} bf16 dense GEMM (sustained); achieved counts fp32-equivalent flops 2MNK, each issued as 3 "
                            + ('fp16' if f16 else 'TF32') + f" MMAs, so 1/{split:g} of this peak is the ceiling of the parity mode",
             'launches_per_step': conv['n'] // 2, 'ms_per_step': conv['ms'] / 2,

@@ -209,7 +209,10 @@ __device__ __forceinline__ void epilogue_stats(float (&v)[16], bool row_valid, d
 // cross terms.  Each tensor-core accumulate truncates to fp32; spreading the K-blocks over several
 // shorter, smaller-magnitude chains (summed in fp32 round-to-nearest by the epilogue) divides the
 // resulting bias on same-sign data by ~NMAIN at no cost.
-constexpr int TC2_THREADS = 14 * 32;
+// NPW producer warps + TMA + MMA + 4 epilogue warps.  NPW = 16 (2 tile rows per thread instead of 4) doubles the
+// global loads in flight per SM: ncu / timing showed the producers' K-block period (~2400 cycles) to be
+// the L2 latency of their register prefetch ring, not the data pipe or the tensor pipe.
+constexpr int tc2_threads(int npw) { return (npw + 6) * 32; }
 constexpr int TC2_PF_BYTES = 12 * 128;      // weight-tile L2 prefetch distance, in bytes of K per row
 
 template <int BN> struct Tc2Cfg {
@@ -225,15 +228,19 @@ template <int BN> struct Tc2Cfg {
 
 struct Tc2Work { int m_tiles, n_tiles, total; };
 
-template <int BN, int KIND>
-__global__ void __launch_bounds__(TC2_THREADS, 1)
+template <int BN, int KIND, int NPW>
+__global__ void __maxnreg__(NPW == 16 ? 88 : 128)       // 704 x 88 / 448 x 128 registers: one CTA per SM either way
 conv_tc2_kernel(const ConvTcP p, const Tc2Work wk, const __grid_constant__ CUtensorMap map_hi,
                 const __grid_constant__ CUtensorMap map_lo) {
     using Cfg = Tc2Cfg<BN>;
     using KC = KindCfg<KIND>;
     constexpr int STAGES = Cfg::STAGES;
     constexpr int NMAIN = Cfg::NMAIN;
-    constexpr int BK = KC::BK, NV = KC::NV, RING = KC::RING;
+    constexpr int BK = KC::BK, NV = KC::NV;
+    constexpr int ROWS = 32 / NPW;                       // tile rows per producer thread (4 or 2)
+    constexpr int RSTEP = NPW * 4;                       // rows r0 + RSTEP*j
+    constexpr int RING = NPW == 16 ? KC::RING + 1 : KC::RING;       // register prefetch ring (K-blocks); RING-1 in flight
+    constexpr int W_TMA = NPW, W_MMA = NPW + 1;          // warp roles; epilogue = the four warps after W_MMA
     constexpr int PF = TC2_PF_BYTES / 128;     // K-blocks
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -251,9 +258,9 @@ conv_tc2_kernel(const ConvTcP p, const Tc2Work wk, const __grid_constant__ CUten
     volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(base_ptr + STAGES * Cfg::STAGE_BYTES + 8 * (3 * STAGES + 4));
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    if (warp == 8 && lane == 0) {
+    if (warp == W_TMA && lane == 0) {
         for (int s = 0; s < STAGES; ++s) {
-            mbar_init(full_a(s), 8);          // the 8 producer warps
+            mbar_init(full_a(s), NPW);        // the producer warps
             mbar_init(full_b(s), 1);
             mbar_init(empty(s), 1);
         }
@@ -262,7 +269,7 @@ conv_tc2_kernel(const ConvTcP p, const Tc2Work wk, const __grid_constant__ CUten
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_hi) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_lo) : "memory");
     }
-    if (warp == 9) {
+    if (warp == W_MMA) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
                      ::"r"(smem_u32((const void*)tmem_slot)), "n"(Cfg::TMEM_COLS) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -279,12 +286,12 @@ conv_tc2_kernel(const ConvTcP p, const Tc2Work wk, const __grid_constant__ CUten
         sp = w / wk.m_tiles;
     };
 
-    if (warp < 8) {
+    if (warp < NPW) {
         // =============================== A producers ===============================
-        // All 8 warps fill every K-block: 4 rows x one 16-byte smem chunk (4 or 8 channels) per thread.
+        // All producer warps fill every K-block: ROWS rows x one 16-byte smem chunk (4 or 8 channels) per thread.
         const int chunk = threadIdx.x & 7;
         const int cofs = chunk * 4;                        // this thread's channels inside the K-block: [cofs, cofs+4) (+32 for the 2nd load)
-        const int r0 = threadIdx.x >> 3;                   // rows r0 + 32*j, j = 0..3
+        const int r0 = threadIdx.x >> 3;                   // rows r0 + RSTEP*j, j < ROWS
         int git = 0;                                       // global K-block counter of this CTA
         for (int w = blockIdx.x; w < wk.total; w += gridDim.x) {
             int mt, nt, sp;
@@ -292,12 +299,12 @@ conv_tc2_kernel(const ConvTcP p, const Tc2Work wk, const __grid_constant__ CUten
             const int m_base = mt * TC_BM;
             const int kb_begin = sp * p.kb_per_split;
             const int nkb = min(p.kblocks, kb_begin + p.kb_per_split) - kb_begin;
-            int rb[4], rsp[4], rc[4];
+            int rb[ROWS], rsp[ROWS], rc[ROWS];
             unsigned rvmask = 0;
             const long long plane_sz = (long long)p.D * p.H * p.W;
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                int m = m_base + r0 + 32 * j;
+            for (int j = 0; j < ROWS; ++j) {
+                int m = m_base + r0 + RSTEP * j;
                 const bool v = m < p.M;
                 if (!v) m = 0;
                 const int xo = m % p.Wo; m /= p.Wo;
@@ -317,14 +324,14 @@ conv_tc2_kernel(const ConvTcP p, const Tc2Work wk, const __grid_constant__ CUten
                 kx = tap % p.kw; const int tq = tap / p.kw; ky = tq % p.kh; kz = tq / p.kh;
             }
             // prefetch ring: slot q holds K-block (it % RING == q)
-            float4 v[RING][4][NV];
+            float4 v[RING][ROWS][NV];
             unsigned okm[RING]; int kc[RING]; int ksp[RING];
             auto issue_loads = [&](int q) {
                 const int tap_sp = (kz * p.H + ky) * p.W + kx;
                 okm[q] = 0; kc[q] = c0 + cofs; ksp[q] = tap_sp;
                 const float* xb = p.x + p.ico + cofs + c0;
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
+                for (int j = 0; j < ROWS; ++j) {
                     const int z = ((rc[j] >> 24) & 0xff) - 8 + kz, y = ((rc[j] >> 12) & 0xfff) - 8 + ky, x = (rc[j] & 0xfff) - 8 + kx;
                     const bool inb = ((rvmask >> j) & 1u) && (unsigned)z < (unsigned)p.D && (unsigned)y < (unsigned)p.H &&
                                      (unsigned)x < (unsigned)p.W;
@@ -347,7 +354,7 @@ conv_tc2_kernel(const ConvTcP p, const Tc2Work wk, const __grid_constant__ CUten
                 if (p.pro != G6D_PRO_NONE) {
                     const bool relu = p.pro == G6D_PRO_AFFINE_RELU;
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) {
+                    for (int j = 0; j < ROWS; ++j) {
                         if (okm[q] & (1u << j)) {
                             const float4* scp; const float4* shp;
                             if (p.pro == G6D_PRO_CORR) {
@@ -365,8 +372,8 @@ conv_tc2_kernel(const ConvTcP p, const Tc2Work wk, const __grid_constant__ CUten
                 }
                 mbar_wait(empty(s), (n_use & 1) ^ 1, 1, g_it);
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const int r = r0 + 32 * j;
+                for (int j = 0; j < ROWS; ++j) {
+                    const int r = r0 + RSTEP * j;
                     const uint32_t so = r * 128 + ((chunk ^ (r & 7)) << 4);        // Swizzle<3,4,3>
                     split_store<KIND>(a_hi(s) + so, a_lo(s) + so, v[q][j]);
                 }
@@ -389,7 +396,7 @@ conv_tc2_kernel(const ConvTcP p, const Tc2Work wk, const __grid_constant__ CUten
             }
             git += nkb;
         }
-    } else if (warp == 8) {
+    } else if (warp == W_TMA) {
         // =============================== B producer (TMA) ===============================
         if (lane == 0) {
             int git = 0;
@@ -419,7 +426,7 @@ conv_tc2_kernel(const ConvTcP p, const Tc2Work wk, const __grid_constant__ CUten
                 }
             }
         }
-    } else if (warp == 9) {
+    } else if (warp == W_MMA) {
         // =============================== MMA issuer ===============================
         if (elect_one_sync()) {
             const uint32_t idesc = umma_idesc<KIND>(TC_BM, BN);
@@ -455,7 +462,7 @@ conv_tc2_kernel(const ConvTcP p, const Tc2Work wk, const __grid_constant__ CUten
             }
         }
     } else {
-        // =============================== epilogue (warps 10-13) ===============================
+        // =============================== epilogue (the 4 warps after the MMA warp) ===============================
         const int quad = warp & 3;                     // TMEM lane quadrant = warp id % 4
         int tile = 0;
         for (int w = blockIdx.x; w < wk.total; w += gridDim.x, ++tile) {
@@ -497,11 +504,22 @@ conv_tc2_kernel(const ConvTcP p, const Tc2Work wk, const __grid_constant__ CUten
                 }
                 const int n0 = n_base + cc;
                 if (!partial) {
+                    if (p.bias) {
+                        if (vec_ok && n0 + 16 <= p.Cout) {          // 4 x 128-bit (L1-broadcast) bias loads
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) {
-                        float v = accv[j];
-                        if (p.bias && n0 + j < p.Cout) v += __ldg(p.bias + n0 + j);
-                        accv[j] = tc_act(v, p.act);
+                            for (int j4 = 0; j4 < 4; ++j4) {
+                                const float4 bb = __ldg(reinterpret_cast<const float4*>(p.bias + n0) + j4);
+                                accv[j4 * 4] += bb.x; accv[j4 * 4 + 1] += bb.y; accv[j4 * 4 + 2] += bb.z; accv[j4 * 4 + 3] += bb.w;
+                            }
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 16; ++j)
+                                if (n0 + j < p.Cout) accv[j] += __ldg(p.bias + n0 + j);
+                        }
+                    }
+                    if (p.act != G6D_ACT_NONE) {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) accv[j] = tc_act(accv[j], p.act);
                     }
                 }
                 if (m < p.M) {
@@ -526,7 +544,7 @@ conv_tc2_kernel(const ConvTcP p, const Tc2Work wk, const __grid_constant__ CUten
         }
     }
     __syncthreads();
-    if (warp == 9) {
+    if (warp == W_MMA) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_acc), "n"(Cfg::TMEM_COLS) : "memory");
     }
@@ -689,12 +707,20 @@ static int fill_tc_params(const g6d_conv_desc* d, int kind, ConvTcP& p) {
     return G6D_OK;
 }
 
-template <int BN, int KIND>
+// G6D_CONV_NPW = 8 | 16 producer warps of the persistent kernel (default 16)
+static int tc2_npw() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("G6D_CONV_NPW"); v = (e && e[0] == '8') ? 8 : 16; }
+    return v;
+}
+
+template <int BN, int KIND, int NPW = 16>
 static int launch_tc2(const ConvTcP& p, const CUtensorMap& mh, const CUtensorMap& ml, cudaStream_t st) {
+    if (NPW == 16 && tc2_npw() == 8) return launch_tc2<BN, KIND, 8>(p, mh, ml, st);
     using Cfg = Tc2Cfg<BN>;
     static bool configured = false;
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(conv_tc2_kernel<BN, KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+        cudaError_t e = cudaFuncSetAttribute(conv_tc2_kernel<BN, KIND, NPW>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
         if (e != cudaSuccess) { set_error("g6d_conv_tc: cannot opt in to %d B of shared memory: %s", Cfg::SMEM_BYTES, cudaGetErrorString(e)); return G6D_ECUDA; }
         configured = true;
     }
@@ -703,7 +729,7 @@ static int launch_tc2(const ConvTcP& p, const CUtensorMap& mh, const CUtensorMap
     const long long total = (long long)wk.m_tiles * wk.n_tiles * p.splits;
     wk.total = (int)total;
     const int grid = total < kNumSMs ? (int)total : kNumSMs;
-    conv_tc2_kernel<BN, KIND><<<grid, TC2_THREADS, Cfg::SMEM_BYTES, st>>>(p, wk, mh, ml);
+    conv_tc2_kernel<BN, KIND, NPW><<<grid, tc2_threads(NPW), Cfg::SMEM_BYTES, st>>>(p, wk, mh, ml);
     G6D_CHECK_LAUNCH("g6d_conv_tc");
     return G6D_OK;
 }
@@ -862,57 +888,86 @@ conv_tcflat_kernel(const ConvFlatP p, const __grid_constant__ CUtensorMap map_hi
         const long long plane = (long long)p.H * p.W;
         const long long gi = (long long)b / p.group_rows;
         const bool relu = p.pro == G6D_PRO_AFFINE_RELU;
-        for (int u = 0; u < nunits; ++u) {
-            const int cb = cb_begin + u / p.nseg, seg = u % p.nseg;
-            const int s = u % p.a_stages;
-            const uint32_t n_use = u / p.a_stages;
+        // Software pipeline over (unit, 128-row trip) with a ring of NB register slots: the global loads of
+        // the next NB-1 trips (possibly of the next unit: they only touch registers, so they do not wait for
+        // the stage to be free) are in flight while a trip is transformed and stored.  Without it every trip
+        // paid a full L2 round trip before its first st.shared.
+        constexpr int NB = 3;
+        const int trips = (p.seg_rows + 127) / 128;
+        const int total = nunits * trips;
+        float4 v[NB][4][NV]; int off[NB][4];
+        auto unit_of = [&](int tt, int& u, int& rbase, int& cb, int& kz, int& tb) {
+            u = tt / trips; rbase = (tt - u * trips) * 128;
+            cb = cb_begin + u / p.nseg;
+            const int seg = u % p.nseg;
             // FLAT: seg = kz, table 0.  ROW: seg = kz*kh + ky, table ky.
-            const int kz = p.mode == 1 ? seg / p.kh : seg;
-            const int tb = p.mode == 1 ? seg % p.kh : 0;
+            kz = p.mode == 1 ? seg / p.kh : seg;
+            tb = p.mode == 1 ? seg % p.kh : 0;
+        };
+        auto issue = [&](int tt, int q) {
+            int u, rbase, cb, kz, tb;
+            unit_of(tt, u, rbase, cb, kz, tb);
             const int zz = zo + kz - p.pd;
             const bool zok = (unsigned)zz < (unsigned)p.D;
-            const int c = cb * BK + cofs;
-            const float* xplane = p.x + ((long long)b * p.D + (zok ? zz : 0)) * plane * p.ics + p.ico + c;
+            const float* xplane = p.x + ((long long)b * p.D + (zok ? zz : 0)) * plane * p.ics + p.ico + cb * BK + cofs;
             const int* tab = rowtab + tb * p.seg_rows;
-            mbar_wait(a_empty(s), (n_use & 1) ^ 1, 1, u);
-            for (int rbase = 0; rbase < p.seg_rows; rbase += 128) {        // 4 rows per thread per trip
-                float4 v[4][NV]; int off[4];
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const int r = rbase + r0 + 32 * j;
-                    off[j] = (r < p.seg_rows && zok) ? tab[r] : -1;
+            for (int j = 0; j < 4; ++j) {
+                const int r = rbase + r0 + 32 * j;
+                off[q][j] = (r < p.seg_rows && zok) ? tab[r] : -1;
 #pragma unroll
-                    for (int e = 0; e < NV; ++e) v[j][e] = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (off[j] >= 0) {
-                        const float4* src = reinterpret_cast<const float4*>(xplane + (long long)off[j] * p.ics);
+                for (int e = 0; e < NV; ++e) v[q][j][e] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (off[q][j] >= 0) {
+                    const float4* src = reinterpret_cast<const float4*>(xplane + (long long)off[q][j] * p.ics);
 #pragma unroll
-                        for (int e = 0; e < NV; ++e) v[j][e] = __ldg(src + e * 8);
-                    }
-                }
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const int r = rbase + r0 + 32 * j;
-                    if (r >= p.rows_pad) continue;
-                    if (p.pro != G6D_PRO_NONE && off[j] >= 0) {
-                        const float4* scp; const float4* shp;
-                        if (p.pro == G6D_PRO_CORR) {
-                            const long long sp = (long long)zz * plane + off[j];
-                            scp = reinterpret_cast<const float4*>(p.ps + sp * p.Cin + c);
-                            shp = reinterpret_cast<const float4*>(p.pb + c);
-                        } else {
-                            scp = reinterpret_cast<const float4*>(p.ps + gi * p.Cin + c);
-                            shp = reinterpret_cast<const float4*>(p.pb + gi * p.Cin + c);
-                        }
-#pragma unroll
-                        for (int e = 0; e < NV; ++e) v[j][e] = affine4(v[j][e], __ldg(scp + e * 8), __ldg(shp + e * 8), relu);
-                    }
-                    const uint32_t so = r * 128 + ((chunk ^ (r & 7)) << 4);
-                    split_store<KIND>(a_hi(s) + so, a_lo(s) + so, v[j]);
+                    for (int e = 0; e < NV; ++e) v[q][j][e] = __ldg(src + e * 8);
                 }
             }
-            fence_proxy_async();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(a_full(s));
+        };
+        auto store = [&](int tt, int q) {
+            int u, rbase, cb, kz, tb;
+            unit_of(tt, u, rbase, cb, kz, tb);
+            const int s = u % p.a_stages;
+            const int zz = zo + kz - p.pd;
+            const int c = cb * BK + cofs;
+            if (rbase == 0) mbar_wait(a_empty(s), ((u / p.a_stages) & 1) ^ 1, 1, u);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int r = rbase + r0 + 32 * j;
+                if (r >= p.rows_pad) continue;
+                if (p.pro != G6D_PRO_NONE && off[q][j] >= 0) {
+                    const float4* scp; const float4* shp;
+                    if (p.pro == G6D_PRO_CORR) {
+                        const long long sp = (long long)zz * plane + off[q][j];
+                        scp = reinterpret_cast<const float4*>(p.ps + sp * p.Cin + c);
+                        shp = reinterpret_cast<const float4*>(p.pb + c);
+                    } else {
+                        scp = reinterpret_cast<const float4*>(p.ps + gi * p.Cin + c);
+                        shp = reinterpret_cast<const float4*>(p.pb + gi * p.Cin + c);
+                    }
+#pragma unroll
+                    for (int e = 0; e < NV; ++e) v[q][j][e] = affine4(v[q][j][e], __ldg(scp + e * 8), __ldg(shp + e * 8), relu);
+                }
+                const uint32_t so = r * 128 + ((chunk ^ (r & 7)) << 4);
+                split_store<KIND>(a_hi(s) + so, a_lo(s) + so, v[q][j]);
+            }
+            if (rbase + 128 >= p.seg_rows) {          // last trip of the unit: publish the stage
+                fence_proxy_async();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(a_full(s));
+            }
+        };
+#pragma unroll
+        for (int q = 0; q < NB - 1; ++q)
+            if (q < total) issue(q, q);
+        for (int tt = 0; tt < total; tt += NB) {
+#pragma unroll
+            for (int q = 0; q < NB; ++q) {
+                if (tt + q < total) {
+                    if (tt + q + NB - 1 < total) issue(tt + q + NB - 1, (q + NB - 1) % NB);
+                    store(tt + q, q);
+                }
+            }
         }
 
         // =============================== epilogue ===============================
@@ -955,11 +1010,22 @@ conv_tcflat_kernel(const ConvFlatP p, const __grid_constant__ CUtensorMap map_hi
             }
             const int n0 = n_base + col0 + cc;
             if (!partial) {
+                if (p.bias) {
+                    if (vec_ok && n0 + 16 <= p.Cout) {
 #pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                    float v = accv[j];
-                    if (p.bias && n0 + j < p.Cout) v += __ldg(p.bias + n0 + j);
-                    accv[j] = tc_act(v, p.act);
+                        for (int j4 = 0; j4 < 4; ++j4) {
+                            const float4 bb = __ldg(reinterpret_cast<const float4*>(p.bias + n0) + j4);
+                            accv[j4 * 4] += bb.x; accv[j4 * 4 + 1] += bb.y; accv[j4 * 4 + 2] += bb.z; accv[j4 * 4 + 3] += bb.w;
+                        }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j)
+                            if (n0 + j < p.Cout) accv[j] += __ldg(p.bias + n0 + j);
+                    }
+                }
+                if (p.act != G6D_ACT_NONE) {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) accv[j] = tc_act(accv[j], p.act);
                 }
             }
             if (valid) {

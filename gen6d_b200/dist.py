@@ -25,6 +25,11 @@ class Comm:
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.backend = dist.get_backend(group) if dist.is_initialized() else 'none'
+        # NCCL collectives are stream-ordered kernels: they can be captured into the stage's CUDA graph and
+        # issued from branch streams (every rank issues them in the same host order); gloo stages through
+        # the host and must run eagerly.  G6D_SHARD_GRAPHS=0 forces the eager path.
+        self.capturable = self.backend == 'nccl' and os.environ.get('G6D_SHARD_GRAPHS', '1') != '0'
+        self.calls = {'all_reduce': 0, 'all_gather': 0}
 
     def _stage(self, t):
         return t.cpu() if (self.backend == 'gloo' and t.is_cuda) else t
@@ -32,6 +37,7 @@ class Comm:
     def all_reduce_sum(self, t):
         if self.world == 1:
             return t
+        self.calls['all_reduce'] += 1
         s = self._stage(t).contiguous()
         dist.all_reduce(s, op=dist.ReduceOp.SUM, group=self.group)
         return s.to(t.device)
@@ -40,7 +46,14 @@ class Comm:
         """Concatenate equally-shaped shards in rank order along `dim`."""
         if self.world == 1:
             return t
+        self.calls['all_gather'] += 1
         s = self._stage(t).contiguous()
+        if self.backend == 'nccl':          # one collective into one buffer (rank-major), no per-rank temporaries
+            out = torch.empty((self.world,) + tuple(s.shape), device=s.device, dtype=s.dtype)
+            dist.all_gather_into_tensor(out, s, group=self.group)
+            if dim == 0:
+                return out.reshape((self.world * s.shape[0],) + tuple(s.shape[1:]))
+            return out.movedim(0, dim).reshape(tuple(s.shape[:dim]) + (self.world * s.shape[dim],) + tuple(s.shape[dim + 1:]))
         parts = [torch.empty_like(s) for _ in range(self.world)]
         dist.all_gather(parts, s, group=self.group)
         return torch.cat(parts, dim).to(t.device)

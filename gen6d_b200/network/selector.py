@@ -21,7 +21,7 @@ IN_EPS = 1e-5
 
 class LocalComm:
     """Single-process stand-in for gen6d_b200.dist.Comm (no sharding)."""
-    rank, world = 0, 1
+    rank, world, capturable = 0, 1, True
 
     def all_reduce_sum(self, t):
         return t
@@ -135,6 +135,10 @@ class ViewpointSelector(PackedModule):
         self.ref_pose_embed = x.reshape(rfn, 512)
         self.bump_generation()          # captured graphs / worker clones hold pointers to the previous reference set
 
+    def comm_stats(self):
+        """Collectives issued per query by the sharded path (counted on the last eager / capture pass)."""
+        return dict(getattr(self.comm, 'calls', {}))
+
     def _s2_counters(self):
         """Completion counters of the fused S2 kernel: zero between calls (the kernel restores that), private
         to this handle (worker clones run concurrently on other streams and get their own)."""
@@ -180,7 +184,7 @@ class ViewpointSelector(PackedModule):
         feats = torch.empty(S, FEAT_PAD, device=dev, dtype=torch.float32)      # cols 0-511: cf3, 512-514 + pad: vp_norm
         scores = ops.sel_corr_score3([r.reshape(S, -1, r.shape[-1]) for r in self.ref_feats_cache],
                                      [q.reshape(-1, q.shape[-1]) for q in q_feats], counters=self._s2_counters())
-        br = Branches(3 if self.comm.world == 1 else 1)     # the three towers only meet in cat_buf
+        br = Branches(3 if self.comm.capturable else 1)     # the three towers only meet in cat_buf (NCCL: collectives ride the branch streams)
         keep = []
 
         def one_level(l, q, ref, s1, s2):
@@ -306,10 +310,10 @@ class ViewpointSelector(PackedModule):
         fn = self._select_warped(size)
         with torch.no_grad():
             jobs = self._to_dev(G.pack_warp_jobs([frame_dev], [G.affine_dst_to_src(M)]))
-            if self.comm.world == 1:
+            if self.comm.capturable:
                 crop, idx, out, logits = self.stages.run(f'select_warp{size}', fn, [jobs])
             else:
-                crop, idx, out, logits = fn(jobs)           # collectives inside: run eagerly
+                crop, idx, out, logits = fn(jobs)           # host-staged collectives inside: run eagerly
             crop, idx, out, logits = [self._to_host(t) for t in (crop, idx, out, logits)]
         return {'ref_idx': idx, 'angles': out[:, 0].copy(), 'scores': logits, 'que_imgs': crop}
 
@@ -320,7 +324,7 @@ class ViewpointSelector(PackedModule):
         fn = self._select_warped(size)
         with torch.no_grad():
             jobs = self._to_dev(G.pack_warp_jobs([frames_dev[i] for i in range(len(Ms))], [G.affine_dst_to_src(M) for M in Ms]))
-            if self.comm.world == 1:
+            if self.comm.capturable:
                 crop, idx, out, logits = self.stages.run(f'select_warp{size}', fn, [jobs])
             else:
                 crop, idx, out, logits = fn(jobs)
@@ -332,9 +336,9 @@ class ViewpointSelector(PackedModule):
         (selector.py:165-175; the angle is returned un-rescaled, as the reference does)"""
         with torch.no_grad():
             u8 = self._to_dev(que_imgs)
-            if self.comm.world == 1:
+            if self.comm.capturable:    # NCCL collectives are captured with the kernels; gloo (host-staged) runs eagerly
                 idx, out, logits = self.stages.run('select', self._select_u8, [u8])
             else:
-                idx, out, logits = self._select_u8(u8)      # collectives inside: run eagerly
+                idx, out, logits = self._select_u8(u8)
             idx, out, logits = self._to_host(idx), self._to_host(out), self._to_host(logits)
         return {'ref_idx': idx, 'angles': out[:, 0].copy(), 'scores': logits}

@@ -1,6 +1,7 @@
-"""Reference-sharded selector and pose-sharded refiner with 2 ranks.  On the 1-GPU test box both
-ranks share cuda:0 and talk over gloo (tensors staged through the host); on a multi-GPU box the
-same code runs one rank per GPU over NCCL (bench / dist.init_from_env)."""
+"""Reference-sharded selector and pose-sharded refiner with 2 ranks: one rank per GPU over NCCL when
+the box has >= 2 GPUs (the collectives are then captured into the select stage's CUDA graph and ride
+the branch streams); on a 1-GPU box both ranks share cuda:0 and talk over gloo (tensors staged through
+the host, eager)."""
 import os
 import socket
 
@@ -26,15 +27,21 @@ def _worker(rank, world, port, q):
     import sys
     here = os.path.dirname(os.path.abspath(__file__))
     sys.path[:0] = [os.path.dirname(here), here]
-    dist.init_process_group('gloo', rank=rank, world_size=world)
+    multi = torch.cuda.device_count() >= world
+    if multi:
+        torch.cuda.set_device(rank)
+        dist.init_process_group('nccl', rank=rank, world_size=world, device_id=torch.device('cuda', rank))
+    else:
+        dist.init_process_group('gloo', rank=rank, world_size=world)
     try:
         from golden import cases
         from gen6d_b200 import ops
         from gen6d_b200.dist import Comm, pose_shard, shard_selector
         from gen6d_b200.network import name2network
         from gen6d_b200.weights import seeded_state_dict
-        torch.cuda.set_device(0)
+        torch.cuda.set_device(rank if multi else 0)
         comm = Comm()
+        assert comm.capturable == multi
 
         def build(name, cfg):
             net = name2network[name](cfg)
@@ -49,6 +56,7 @@ def _worker(rank, world, port, q):
         sharded.load_ref_imgs(c['ref_imgs'], c['ref_poses'], c['object_center'], c['object_vert'])
         assert sharded.ref_shape == (4, 5) and sharded.rfn_total == 8
         got = sharded.select_que_imgs(c['que_imgs'])
+        got = sharded.select_que_imgs(c['que_imgs'])            # second call: graph replay on the NCCL path
         assert got['ref_idx'].tolist() == want['ref_idx'].tolist()
         np.testing.assert_allclose(got['scores'], want['scores'], atol=2e-4)       # exact statistics: not ~0.1 off
         np.testing.assert_allclose(got['angles'], want['angles'], atol=2e-4)
@@ -62,7 +70,7 @@ def _worker(rank, world, port, q):
         whole = rfr._forward_nhwc(*args)
         split = pose_shard(rfr._forward_nhwc, args, comm)
         np.testing.assert_allclose(split.cpu().numpy(), whole.cpu().numpy(), atol=1e-5)
-        q.put((rank, 'ok'))
+        q.put((rank, 'ok nccl' if multi else 'ok gloo'))
     except Exception as e:  # noqa: BLE001
         import traceback
         q.put((rank, traceback.format_exc()))
@@ -80,4 +88,5 @@ def test_sharded_selector_and_pose_shard_match_unsharded():
     res = [q.get(timeout=300) for _ in procs]
     for p in procs:
         p.join(timeout=60)
-    assert all(r[1] == 'ok' for r in res), res
+    assert all(r[1].startswith('ok') for r in res), res
+    print('backend:', res[0][1])
