@@ -32,7 +32,8 @@ import torch
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-E2E_WORKERS = int(os.environ.get('G6D_E2E_WORKERS', '6'))      # frames in flight per GPU (predict_many / device streams)
+E2E_WORKERS = int(os.environ.get('G6D_E2E_WORKERS', '2'))      # host threads / CUDA streams per GPU (predict_many / device lanes)
+E2E_BATCH = int(os.environ.get('G6D_E2E_BATCH', '4'))          # frames per batched stage (predict_batch); WORKERS x BATCH frames in flight
 METRIC = 'poses/sec end-to-end (128^2 crop, 64 refs, 3 refine iters)'
 WORKLOAD = ('full estimator detect->select->3x refine: synthetic 480x640 frame, detector 32 refs x 4 scales, '
             'selector 64 refs x 5 angles, refiner 6 views 32^3 volume, seeded random weights')
@@ -326,45 +327,54 @@ def run_ours(args, rank, world, local_rank):
     frames = [ids[(7 + rank * 13 + i * 3) % len(ids)] for i in range(8)]   # different frames per rank
     K = db.K
 
-    # ---- stage inputs for the device-resident measurement (captured from one real prediction)
-    pose0, inter = est.predict(db.get_image(frames[0]), K)
-    dev = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
-    frame_dev = dev(db.get_image(frames[0]))                     # uint8 [h,w,3], resident
-    _, M_crop = G.crop_similarity(None, inter['det_position'], 1 / inter['det_scale_r2q'], 0, 128)
-    crop_jobs = dev(G.pack_warp_jobs([frame_dev], [G.affine_dst_to_src(M_crop)]))
-    probs = []
-    for p in inter['refine_poses'][:3]:
-        pr = G.refine_problem(db, ids, None, K, p, 128, 6, True, warp=False)
-        srcs = [frame_dev] + est.refiner._ref_images_dev(list(pr['ref_ids']))
-        mats = [G.perspective_dst_to_src(pr['que_H'])] + [G.perspective_dst_to_src(H) for H in pr['ref_Hs']]
-        probs.append((dev(G.pack_warp_jobs(srcs, mats)),) + tuple(dev(pr[k][None]) for k in ('que_K', 'que_pose', 'ref_Ks', 'ref_poses')))
+    # ---- stage inputs for the device-resident measurement: every captured stage of one real batched
+    # prediction (detect [B frames] -> select [B crops, cut on the device] -> 3 x refine [B x 7 crops]) is
+    # recorded with its device-resident inputs and replayed -- exactly what predict_batch launches, minus
+    # host geometry and copies.  W lanes (clones with private graphs, shared weights / reference features),
+    # each on its own stream, keep W x B frames in flight.
+    W, Bt = E2E_WORKERS, E2E_BATCH
+    batch_imgs = [db.get_image(frames[i % len(frames)]) for i in range(Bt)]
+
+    def record(e):
+        rec, mods = [], [m for m in (e.detector, e.selector, e.refiner) if m is not None]
+        for m in mods:
+            def wrapped(name, fn, inputs, _m=m, _o=m.stages.run):
+                rec.append((_m, name, fn, list(inputs)))
+                return _o(name, fn, inputs)
+            m.stages.run = wrapped
+        try:
+            e.predict_batch(batch_imgs, [K] * Bt)
+        finally:
+            for m in mods:
+                del m.stages.run
+        return rec
+
+    lanes = [torch.cuda.Stream() for _ in range(W)]
+    recs = []
+    for i in range(W):
+        e = est if i == 0 else est.worker_clone()
+        with torch.cuda.stream(lanes[i]):
+            recs.append(record(e))
+            lanes[i].synchronize()
     det, sel, rfr = est.detector, est.selector, est.refiner
 
-    # W independent frames in flight, each on its own stream with its own captured stage graphs
-    # (shared weights / reference features): at batch 1 many kernels launch fewer CTAs than SMs,
-    # so concurrent frames are what fills the machine.  Results stay on the device.
-    W = E2E_WORKERS
-    nets = [(det, sel, rfr)] + [(det.worker_clone(), sel.worker_clone(), rfr.worker_clone()) for _ in range(W - 1)]
-    lanes = [torch.cuda.Stream() for _ in range(W)]
-
-    def device_step(i=0, eager=False):
-        """The three-network path on device-resident inputs (through the captured stage graphs,
-        exactly what predict() launches, minus host geometry and copies)."""
-        d, sl, r = nets[0] if eager else nets[i % W]
-        run = (lambda m, name, fn, a: fn(*a)) if eager else (lambda m, name, fn, a: m.stages.run(name, fn, a))
+    def device_batch(i=0, eager=False):
+        """One batch of Bt poses on lane i through the captured stage graphs (eager=True: kernel by kernel)."""
         with torch.no_grad():
-            run(d, 'detect', d._detect_u8, [frame_dev[None]])
-            run(sl, 'select_warp128', sl._select_warped(128), [crop_jobs])          # detection crop + selector
-            for pr in probs:
-                run(r, 'refine_warp128', r._refine_warped(128), list(pr))            # 7 look-at crops + refiner
+            for m, name, fn, inputs in recs[0 if eager else i % W]:
+                if eager:
+                    fn(*inputs)
+                else:
+                    m.stages.run(name, fn, inputs)
 
     def device_steps(n):
+        """n poses = ceil(n / Bt) batches dealt round-robin to the lanes (a short last batch runs full)."""
         main = torch.cuda.current_stream()
         for st in lanes:
             st.wait_stream(main)
-        for i in range(n):
+        for i in range((n + Bt - 1) // Bt):
             with torch.cuda.stream(lanes[i % W]):
-                device_step(i)
+                device_batch(i)
         for st in lanes:
             main.wait_stream(st)
 
@@ -405,7 +415,7 @@ def run_ours(args, rank, world, local_rank):
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    dev_ms, _, launches = timed(device_steps, args.steps, max(args.warmup, 2 * W), batched=True)
+    dev_ms, _, launches = timed(device_steps, args.steps, max(args.warmup, 2 * W * Bt), batched=True)
 
     # ---- end to end through the public API (numpy in, numpy out)
     imgs = [db.get_image(f) for f in frames]
@@ -420,13 +430,13 @@ def run_ours(args, rank, world, local_rank):
     io = dict(nbase.IO_BYTES)
     n_calls = args.steps + args.warmup
 
-    # the throughput API: the same per-frame predict(), two frames in flight on one GPU
+    # the throughput API: W host threads x batches of Bt frames through predict_batch
     def pipelined(n):
-        res = est.predict_many([imgs[i % len(imgs)] for i in range(n)], [K] * n, workers=E2E_WORKERS)
+        res = est.predict_many([imgs[i % len(imgs)] for i in range(n)], [K] * n, workers=E2E_WORKERS, batch=E2E_BATCH)
         out_poses.extend(r[0] for r in res)
 
-    pipelined(2 * E2E_WORKERS)                         # builds the worker clones, captures their graphs
-    pipelined(max(args.warmup, E2E_WORKERS))           # untimed warm-up of the whole pipelined path
+    pipelined(2 * E2E_WORKERS * E2E_BATCH)             # builds the worker clones, captures their graphs
+    pipelined(max(args.warmup, E2E_WORKERS * E2E_BATCH))   # untimed warm-up of the whole pipelined path
     barrier()
     t0 = time.perf_counter()
     pipelined(args.steps)
@@ -447,13 +457,12 @@ def run_ours(args, rank, world, local_rank):
 
     # ---- live kernel timing (CUDA events around every launch of the three kernels of interest)
     os.environ['G6D_BRANCH_STREAMS'] = '0'      # per-kernel timing: one kernel at a time, no co-scheduling
-    device_step(0, eager=True)
+    device_batch(0, eager=True)
     torch.cuda.synchronize()
     prof = ops.enable_profiling()
     pe0, pe1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     pe0.record()
-    for _ in range(2):
-        device_step(0, eager=True)
+    device_batch(0, eager=True)
     pe1.record()
     torch.cuda.synchronize()
     eager_ms = pe0.elapsed_time(pe1)
@@ -473,11 +482,12 @@ def run_ours(args, rank, world, local_rank):
                           'its 4.2 GB of operand reads are served from L2; activations + weights come from HBM once',
             'peak_source': f"{peaks['src']} bf16 dense GEMM (sustained); achieved counts fp32-equivalent flops 2MNK, each issued as 3 "
                            + ('fp16' if f16 else 'TF32') + f" MMAs, so 1/{split:g} of this peak is the ceiling of the parity mode",
-            'launches_per_step': conv['n'] // 2, 'ms_per_step': conv['ms'] / 2,
+            'launches_per_step': conv['n'] / Bt, 'ms_per_step': conv['ms'] / Bt,
             'share_of_step': conv['ms'] / max(eager_ms, 1e-9),
-            'timing': 'CUDA events around every launch in an extra serialised pass (branch streams off, one frame): ms_per_step here '
-                      'is un-overlapped kernel time and exceeds the top-level ms_per_step, which overlaps frames and branches',
-            'ffma_fallback': {'launches_per_step': ffma['n'] // 2, 'ms_per_step': ffma['ms'] / 2,
+            'timing': f'CUDA events around every launch in an extra serialised pass (branch streams off, one batch of {Bt} frames, kernel by '
+                      'kernel): ms_per_step here is un-overlapped kernel time per pose and exceeds the top-level ms_per_step, which overlaps '
+                      'lanes and branches',
+            'ffma_fallback': {'launches_per_step': ffma['n'] / Bt, 'ms_per_step': ffma['ms'] / Bt,
                               'tflops': ffma['work'] / max(ffma['ms'], 1e-9) / 1e9}}
     roof['frac'] = roof['achieved'] / roof['peak']
     roof['frac_of_split_ceiling'] = roof['achieved'] / (roof['peak'] / split)
@@ -502,14 +512,15 @@ def run_ours(args, rank, world, local_rank):
     line = {'metric': METRIC, 'value': value, 'unit': 'poses/s', 'n_gpus': world, 'steps': args.steps,
             'warmup': args.warmup, 'ms_per_step': dev_ms / args.steps, 'higher_is_better': True, 'scaling': 'weak',
             'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-            'config': {'workload': WORKLOAD, 'parallelism': f'replica x{world} (independent frames per GPU), {E2E_WORKERS} frames in flight per GPU on separate streams',
+            'config': {'workload': WORKLOAD, 'parallelism': f'replica x{world} (independent frames per GPU); per GPU {E2E_WORKERS} lanes (streams) x batches of '
+                                                            f'{E2E_BATCH} frames through the batched stages = {E2E_WORKERS * E2E_BATCH} frames in flight',
                        'l2': 'per-step working set (220 MB selector reference stack + 300 MB weights + detector '
                              'activations) exceeds the 126 MB L2; no explicit flush'},
             'e2e': {'value': world * args.steps / (pipe_ms * 1e-3), 'unit': 'poses/s', 'ms_per_step': pipe_ms / args.steps,
                     'h2d_bytes_per_step': io['h2d'] // n_calls, 'd2h_bytes_per_step': io['d2h'] // n_calls,
-                    'api': f'Gen6DEstimator.predict_many(numpy frames, Ks, workers={E2E_WORKERS}) -> numpy poses: per frame the same '
-                           'predict() (pinned H2D of the frame once, crops cut from it on the device, camera geometry on the host, D2H of every stage '
-                           f'result), {E2E_WORKERS} frames in flight per GPU',
+                    'api': f'Gen6DEstimator.predict_many(numpy frames, Ks, workers={E2E_WORKERS}, batch={E2E_BATCH}) -> numpy poses: {E2E_WORKERS} host threads '
+                           f'each push batches of {E2E_BATCH} frames through predict_batch (pinned H2D of the frames once, crops cut from them on the device, '
+                           'camera geometry on the host, one D2H per stage and batch)',
                     'single_frame_latency': {'value': e2e_v, 'unit': 'poses/s', 'ms_per_step': e2e_wall_ms / args.steps,
                                              'api': 'Gen6DEstimator.predict(numpy frame, K), one frame at a time'}},
             'gpu_launches': int(launches), 'roofline': roof, 'kernels': extra, 'clocks': clocks}

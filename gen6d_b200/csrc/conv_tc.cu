@@ -209,9 +209,9 @@ __device__ __forceinline__ void epilogue_stats(float (&v)[16], bool row_valid, d
 // cross terms.  Each tensor-core accumulate truncates to fp32; spreading the K-blocks over several
 // shorter, smaller-magnitude chains (summed in fp32 round-to-nearest by the epilogue) divides the
 // resulting bias on same-sign data by ~NMAIN at no cost.
-// NPW producer warps + TMA + MMA + 4 epilogue warps.  NPW = 16 (2 tile rows per thread instead of 4) doubles the
-// global loads in flight per SM: ncu / timing showed the producers' K-block period (~2400 cycles) to be
-// the L2 latency of their register prefetch ring, not the data pipe or the tensor pipe.
+// NPW producer warps + TMA + MMA + 4 epilogue warps.  NPW = 8 is what ships: 16 producer warps (2 tile
+// rows per thread, one more K-block of loads in flight) were measured 25-30 % SLOWER on the large layers
+// (704 threads cap the kernel at 80 registers: the deeper ring spills into the same L1 data pipe).
 constexpr int tc2_threads(int npw) { return (npw + 6) * 32; }
 constexpr int TC2_PF_BYTES = 12 * 128;      // weight-tile L2 prefetch distance, in bytes of K per row
 
@@ -229,7 +229,7 @@ template <int BN> struct Tc2Cfg {
 struct Tc2Work { int m_tiles, n_tiles, total; };
 
 template <int BN, int KIND, int NPW>
-__global__ void __maxnreg__(NPW == 16 ? 88 : 128)       // 704 x 88 / 448 x 128 registers: one CTA per SM either way
+__global__ void __launch_bounds__(tc2_threads(NPW), 1)  // 448 threads x 128 registers, or 704 x 80 (warps allocate registers in units of 512)
 conv_tc2_kernel(const ConvTcP p, const Tc2Work wk, const __grid_constant__ CUtensorMap map_hi,
                 const __grid_constant__ CUtensorMap map_lo) {
     using Cfg = Tc2Cfg<BN>;
@@ -239,7 +239,7 @@ conv_tc2_kernel(const ConvTcP p, const Tc2Work wk, const __grid_constant__ CUten
     constexpr int BK = KC::BK, NV = KC::NV;
     constexpr int ROWS = 32 / NPW;                       // tile rows per producer thread (4 or 2)
     constexpr int RSTEP = NPW * 4;                       // rows r0 + RSTEP*j
-    constexpr int RING = NPW == 16 ? KC::RING + 1 : KC::RING;       // register prefetch ring (K-blocks); RING-1 in flight
+    constexpr int RING = KC::RING;                       // register prefetch ring (K-blocks); RING-1 in flight
     constexpr int W_TMA = NPW, W_MMA = NPW + 1;          // warp roles; epilogue = the four warps after W_MMA
     constexpr int PF = TC2_PF_BYTES / 128;     // K-blocks
     extern __shared__ uint8_t smem_raw[];
@@ -707,16 +707,8 @@ static int fill_tc_params(const g6d_conv_desc* d, int kind, ConvTcP& p) {
     return G6D_OK;
 }
 
-// G6D_CONV_NPW = 8 | 16 producer warps of the persistent kernel (default 16)
-static int tc2_npw() {
-    static int v = -1;
-    if (v < 0) { const char* e = getenv("G6D_CONV_NPW"); v = (e && e[0] == '8') ? 8 : 16; }
-    return v;
-}
-
-template <int BN, int KIND, int NPW = 16>
+template <int BN, int KIND, int NPW = 8>
 static int launch_tc2(const ConvTcP& p, const CUtensorMap& mh, const CUtensorMap& ml, cudaStream_t st) {
-    if (NPW == 16 && tc2_npw() == 8) return launch_tc2<BN, KIND, 8>(p, mh, ml, st);
     using Cfg = Tc2Cfg<BN>;
     static bool configured = false;
     if (!configured) {
