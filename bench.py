@@ -245,7 +245,7 @@ def sharded_section(world, rank):
     refs = per_gpu_refs * world
     poses = cases.sphere_poses(3, refs)
     blocks = (torch.rand(bins, refs, 8, 8, 3, generator=g) * 255).to(torch.uint8).numpy()
-    imgs = np.kron(blocks, np.ones((1, 1, 16, 16, 1), np.uint8))
+    imgs = np.repeat(np.repeat(blocks, 16, axis=2), 16, axis=3)          # blocky 128x128 images, same on every rank
     que = cases.rand_images_u8(5, 1, 128, 128, 3)
     center, vert = np.zeros(3, np.float32), np.array([0, 0, 1], np.float32)
     r0, r1 = comm.shard_range(refs)
@@ -317,12 +317,19 @@ def run_ours(args, rank, world, local_rank):
     from gen6d_b200 import synthetic as syn
     from gen6d_b200.network import base as nbase
 
+    t_start = time.perf_counter()
+
+    def note(what):         # progress on stderr (rank 0): where the wall-clock of a bench run goes
+        if rank == 0:
+            print(f'[bench {time.perf_counter() - t_start:6.1f} s] {what}', file=sys.stderr, flush=True)
+
     torch.cuda.set_device(local_rank)
     ops.require_cuda()
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
     est, db = syn.build_estimator()
+    note('estimator built')
     ids = db.get_img_ids()
     frames = [ids[(7 + rank * 13 + i * 3) % len(ids)] for i in range(8)]   # different frames per rank
     K = db.K
@@ -415,8 +422,10 @@ def run_ours(args, rank, world, local_rank):
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
+    note('stage graphs recorded')
     dev_ms, _, launches = timed(device_steps, args.steps, max(args.warmup, 2 * W * Bt), batched=True)
 
+    note('device-resident timing done')
     # ---- end to end through the public API (numpy in, numpy out)
     imgs = [db.get_image(f) for f in frames]
     nbase.IO_BYTES['h2d'] = nbase.IO_BYTES['d2h'] = 0
@@ -430,6 +439,7 @@ def run_ours(args, rank, world, local_rank):
     io = dict(nbase.IO_BYTES)
     n_calls = args.steps + args.warmup
 
+    note('single-frame e2e done')
     # the throughput API: W host threads x batches of Bt frames through predict_batch
     def pipelined(n):
         res = est.predict_many([imgs[i % len(imgs)] for i in range(n)], [K] * n, workers=E2E_WORKERS, batch=E2E_BATCH)
@@ -455,6 +465,7 @@ def run_ours(args, rank, world, local_rank):
         gathered = [torch.empty_like(mine) for _ in range(world)]
         dist.all_gather(gathered, mine)       # the only collective: results, once, at the end
 
+    note('pipelined e2e done')
     # ---- live kernel timing (CUDA events around every launch of the three kernels of interest)
     os.environ['G6D_BRANCH_STREAMS'] = '0'      # per-kernel timing: one kernel at a time, no co-scheduling
     device_batch(0, eager=True)
@@ -503,8 +514,11 @@ def run_ours(args, rank, world, local_rank):
                           'algorithmic_bytes_per_launch': s['work'] / s['n'],
                           'traffic': traffic.get('s2' if 'score3' in key else 'r2')})
 
+    note('kernel timing done')
     accuracy = add_accuracy(est, db) if rank == 0 else None
+    note('accuracy done')
     sharded = sharded_section(world, rank) if world > 1 else None
+    note('sharded section done')
     if rank != 0:
         return
     value = world * args.steps / (dev_ms * 1e-3)

@@ -173,6 +173,55 @@ class ViewpointSelector(PackedModule):
             pro = ops.PRO_AFFINE_RELU if 'r' in post else ops.PRO_AFFINE
             x = ops.maxpool2x2(y) if 'p' in post else y
 
+    def _towers_sharded(self, q_feats, cat_buf, S, S_total):
+        """The three towers with the reference axis sharded over GPUs, ROUND-synchronous: round r runs the
+        r-th convolution of every tower that still has one (concurrently, on branch streams), then ONE
+        all-reduce carries the InstanceNorm moments of all of them (5 rounds for the 6 + 4 + 2 convolutions
+        instead of 9 per-layer all-reduces).  Same arithmetic as _tower."""
+        towers = self.packed()['towers']
+        nbr = 3 if self.comm.capturable else 1
+        state, keep = [], []
+        for l, (q, ref, (s1, s2)) in enumerate(zip(q_feats, self.ref_feats_cache, self.ref_sums)):
+            h, w, c = q.shape
+            scale, shift = ops.sel_corr_prologue(q.reshape(h * w, c), s1, s2, S_total, IN_EPS)
+            state.append({'x': ref, 'pro': ops.PRO_CORR, 'ps': scale, 'pb': shift, 'i': 0})
+        for _ in range(max(len(t) for t in towers)):
+            br = Branches(nbr)          # forks from the main stream: after the previous round's finalize / pool kernels
+            pend = []
+            for l, st in enumerate(state):
+                convs = towers[l]
+                if st['i'] >= len(convs):
+                    continue
+                pc, post = convs[st['i']]
+                last = st['i'] + 1 == len(convs)
+
+                def step(l=l, st=st, pc=pc, last=last):
+                    if last:
+                        ops.conv(st['x'], pc, prologue=st['pro'], pro_scale=st['ps'], pro_shift=st['pb'], group_rows=S,
+                                 out=cat_buf, out_coff=256 * l)
+                        return None
+                    rows = st['x'].shape[0] * st['x'].shape[1] * st['x'].shape[2]
+                    return ops.conv(st['x'], pc, prologue=st['pro'], pro_scale=st['ps'], pro_shift=st['pb'], group_rows=S,
+                                    stats_rows=rows) + (rows,)
+                res = br.run(l, step)
+                st['i'] += 1
+                if res is not None:
+                    pend.append((st, post, res))
+            br.join()
+            if not pend:
+                continue
+            flat = torch.cat([ws.reshape(-1) for _, _, (_, ws, _) in pend]) if len(pend) > 1 else pend[0][2][1].reshape(-1)
+            flat = self.comm.all_reduce_sum(flat)                 # one collective for every tower's moments of this round
+            o = 0
+            for st, post, (y, ws, rows) in pend:
+                n = ws.numel()
+                ps, pb = ops.instnorm_finalize(flat[o:o + n].reshape(ws.shape), rows // self.ref_shape[0] * self.rfn_total, IN_EPS)
+                o += n
+                keep.append((y, ws))
+                st['ps'], st['pb'] = ps, pb
+                st['pro'] = ops.PRO_AFFINE_RELU if 'r' in post else ops.PRO_AFFINE
+                st['x'] = ops.maxpool2x2(y) if 'p' in post else y
+
     def _select_one(self, q_feats):
         """selector.py:177-215 for one query.  q_feats: 3 x [h, w, 512].  -> logits [rfn], angles [rfn]"""
         p = self.packed()
@@ -184,18 +233,21 @@ class ViewpointSelector(PackedModule):
         feats = torch.empty(S, FEAT_PAD, device=dev, dtype=torch.float32)      # cols 0-511: cf3, 512-514 + pad: vp_norm
         scores = ops.sel_corr_score3([r.reshape(S, -1, r.shape[-1]) for r in self.ref_feats_cache],
                                      [q.reshape(-1, q.shape[-1]) for q in q_feats], counters=self._s2_counters())
-        br = Branches(3 if self.comm.capturable else 1)     # the three towers only meet in cat_buf (NCCL: collectives ride the branch streams)
-        keep = []
+        if self.comm.world == 1:
+            br = Branches(3)                                # the three towers only meet in cat_buf
+            keep = []
 
-        def one_level(l, q, ref, s1, s2):
-            h, w, c = q.shape
-            scale, shift = ops.sel_corr_prologue(q.reshape(h * w, c), s1, s2, S_total, IN_EPS)
-            keep.append((scale, shift))
-            self._tower(l, ref, scale, shift, cat_buf, S)
+            def one_level(l, q, ref, s1, s2):
+                h, w, c = q.shape
+                scale, shift = ops.sel_corr_prologue(q.reshape(h * w, c), s1, s2, S_total, IN_EPS)
+                keep.append((scale, shift))
+                self._tower(l, ref, scale, shift, cat_buf, S)
 
-        for l, (q, ref, (s1, s2)) in enumerate(zip(q_feats, self.ref_feats_cache, self.ref_sums)):
-            br.run(l, lambda l=l, q=q, ref=ref, s1=s1, s2=s2: one_level(l, q, ref, s1, s2))
-        br.join()
+            for l, (q, ref, (s1, s2)) in enumerate(zip(q_feats, self.ref_feats_cache, self.ref_sums)):
+                br.run(l, lambda l=l, q=q, ref=ref, s1=s1, s2=s2: one_level(l, q, ref, s1, s2))
+            br.join()
+        else:
+            self._towers_sharded(q_feats, cat_buf, S, S_total)
         # corr_feats_conv (selector.py:71-77): 1x1 768->512, IN, ReLU, 1x1 512->512, AvgPool(4,4).
         # The second 1x1 conv is linear, so the 4x4 average is taken first (16x less work).
         y, ws = ops.conv(cat_buf, p['cf0'], stats_rows=S * 16)
