@@ -205,7 +205,7 @@ def add_accuracy(est, db):
             'reference': 'unmodified reference estimator on CPU, scored by its utils/pose_utils.py (tests/golden/make_golden_add.py)'}
 
 
-def sharded_section(world, rank):
+def sharded_section(world, rank, note=lambda what: None):
     """BASELINE configs[3] / [4] on the driver's clock (world > 1): selector with the reference views sharded
     (64 refs x 36 rotation bins per GPU = 2304 slices, 1.585 GB stack per GPU; exact cross-GPU InstanceNorm
     statistics) and refiner with the pose batch sharded (32 poses per GPU, 6 views, 32^3).  CUDA events,
@@ -249,14 +249,19 @@ def sharded_section(world, rank):
     que = cases.rand_images_u8(5, 1, 128, 128, 3)
     center, vert = np.zeros(3, np.float32), np.array([0, 0, 1], np.float32)
     r0, r1 = comm.shard_range(refs)
+    note('sharded: inputs synthesised')
     local = build('selector', {'selector_angle_num': bins})
     local.load_ref_imgs(np.ascontiguousarray(imgs[:, r0:r1]), poses[r0:r1], center, vert)
+    note('sharded: unsharded selector loaded')
     t_local = timed(lambda: local.select_que_imgs(que), 5)
+    note('sharded: unsharded selector timed')
     del local
     torch.cuda.empty_cache()
     sel = gdist.shard_selector(build('selector', {'selector_angle_num': bins}), comm)
     sel.load_ref_imgs(imgs, poses, center, vert)
+    note('sharded: sharded selector loaded')
     t_shard = timed(lambda: sel.select_que_imgs(que), 5)
+    note('sharded: sharded selector timed')
     out['selector_ref_shard'] = {
         'workload': f'{refs} refs x {bins} bins over {world} GPUs ({per_gpu_refs} refs = {per_gpu_refs * bins} slices = '
                     f'{per_gpu_refs * bins * 688128 / 1e9:.3f} GB of reference stack per GPU), 1 query 128x128',
@@ -271,6 +276,7 @@ def sharded_section(world, rank):
     dev = lambda x: torch.from_numpy(x).cuda()
     a = [ops.preprocess_u8(dev(rc['que_imgs']), 4, True), dev(rc['que_Ks']), dev(rc['que_poses']),
          ops.preprocess_u8(dev(rc['ref_imgs']), 4, True), dev(rc['ref_Ks']), dev(rc['ref_poses'])]
+    note('sharded: refiner inputs ready')
     with torch.no_grad():
         t_one = timed(lambda: rfr._forward_nhwc(*a), 3, warm=1)
         t_all = timed(lambda: comm.all_gather_cat(rfr._forward_nhwc(*a), dim=0), 3, warm=1)
@@ -517,7 +523,7 @@ def run_ours(args, rank, world, local_rank):
     note('kernel timing done')
     accuracy = add_accuracy(est, db) if rank == 0 else None
     note('accuracy done')
-    sharded = sharded_section(world, rank) if world > 1 else None
+    sharded = sharded_section(world, rank, note) if world > 1 else None
     note('sharded section done')
     if rank != 0:
         return
