@@ -510,16 +510,18 @@ def run_ours(args, rank, world, local_rank):
     roof['frac_of_split_ceiling'] = roof['achieved'] / (roof['peak'] / split)
     roof['frac_of_3xtf32_ceiling'] = roof['achieved'] / (roof['peak'] / 6.0)     # round-1 yardstick, kept for continuity
     extra = []
-    for key, label in (('g6d_sel_corr_score3', 'selector correlation + rotated-similarity score, 3 levels (S2)'),
-                       ('g6d_ref_volume_fill', 'refiner unproject-and-aggregate volume fill (R2)')):
+    for key, label, units in (('g6d_sel_corr_score3', 'selector correlation + rotated-similarity score, 3 levels (S2)', 1),
+                              ('g6d_ref_volume_fill', 'refiner unproject-and-aggregate volume fill (R2)', Bt)):
         if key in stats:
             s = stats[key]
             ach = s['work'] / max(s['ms'], 1e-9) / 1e6
             extra.append({'kernel': label, 'bound': 'hbm', 'achieved': ach, 'peak': peaks['hbm_gbs'], 'unit': 'GB/s',
                           'frac': ach / peaks['hbm_gbs'], 'us_per_launch': s['ms'] / s['n'] * 1e3,
-                          'algorithmic_bytes_per_launch': s['work'] / s['n'],
-                          'traffic': traffic.get('s2' if 'score3' in key else 'r2')})
-
+                          'units_per_launch': units, 'unit_is': 'one query' if units == 1 else 'one pose-iteration (the batched refine stage fills all volumes of the batch in one launch)',
+                          'algorithmic_bytes_per_unit': s['work'] / s['n'] / units,
+                          'traffic': traffic.get('s2' if 'score3' in key else 'r2'),
+                          'traffic_of': 'dram__bytes_read.sum + dram__bytes_write.sum of one launch with ONE unit (ncu --set full on tools/profile_step.py)'
+                                        + ('' if units == 1 else '; the 50 MB the kernel writes per unit stay in L2 for the embed convolutions that read them next')})
     note('kernel timing done')
     accuracy = add_accuracy(est, db) if rank == 0 else None
     note('accuracy done')

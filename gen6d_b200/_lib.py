@@ -74,6 +74,7 @@ _SIGNATURES = {
     'g6d_sel_vp_norm': [P, I, I, F, P, I, I, P],
     'g6d_sel_max_angle_add': [P, P, P, I, I, I, P],
     'g6d_attention': [P, P, P, P, I, I, I, P],
+    'g6d_attention_headmajor': [P, P, P, P, I, I, I, P],
     'g6d_layernorm': [P, P, P, P, I, I, F, P],
     'g6d_sel_parse': [P, P, I, I, P, P, P],
     'g6d_ref_volume_fill': [P, P, P, P, P, P, I, I, I, I, I, I, I, I, P, P, P],

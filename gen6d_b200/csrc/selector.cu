@@ -323,6 +323,92 @@ __global__ void attention_kernel(const float* __restrict__ q, const float* __res
     }
 }
 
+// Tiled attention over HEAD-MAJOR channels (c = head*D + d, D = 64): the layout the selector's packed
+// conv_query / conv_key / conv_feats emit (their output rows are permuted at pack time, conv_merge's input
+// columns likewise, so nothing is transposed at run time).  A block owns (8 query tokens, one head): the
+// K and V tiles of 32 keys x 64 dims are staged in shared memory by coalesced 128-bit loads ONCE per
+// block, scores for all n keys live in shared memory (n <= 2048), softmax(q.k / sqrt(D)) over keys as in
+// attention.py:4-17.  The per-(token, head) kernel above re-reads every key row with a 32-byte stride:
+// 4.3 GB of L2 traffic at n = 512 (a reference-sharded selector over 8 GPUs); this one reads 67 MB.
+constexpr int ATT_TQ = 8, ATT_TK = 32, ATT_D = 64;
+__global__ void __launch_bounds__(128) attention_hm_kernel(const float* __restrict__ q, const float* __restrict__ k,
+                                                           const float* __restrict__ v, float* __restrict__ out, int n, int C) {
+    extern __shared__ float sh[];
+    const int npad = (n + 31) & ~31;
+    float* qs = sh;                                  // [TQ][D]
+    float* kt = qs + ATT_TQ * ATT_D;                 // [TK][D+1]
+    float* sc = kt + ATT_TK * (ATT_D + 1);           // [TQ][npad]
+    __shared__ float s_sum[ATT_TQ];
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    const int i0 = blockIdx.x * ATT_TQ, h = blockIdx.y;
+    const float inv = rsqrtf((float)ATT_D);
+    for (int e = t; e < ATT_TQ * ATT_D; e += 128) {
+        const int qi = e / ATT_D, d = e % ATT_D;
+        qs[e] = i0 + qi < n ? q[(long long)(i0 + qi) * C + h * ATT_D + d] : 0.f;
+    }
+    // ---- scores
+    for (int j0 = 0; j0 < n; j0 += ATT_TK) {
+        __syncthreads();
+        for (int e = t; e < ATT_TK * ATT_D / 4; e += 128) {             // 16 float4 per key row
+            const int jj = e >> 4, d4 = e & 15;
+            float4 kv = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (j0 + jj < n) kv = __ldg(reinterpret_cast<const float4*>(k + (long long)(j0 + jj) * C + h * ATT_D) + d4);
+            float* dst = kt + jj * (ATT_D + 1) + d4 * 4;
+            dst[0] = kv.x; dst[1] = kv.y; dst[2] = kv.z; dst[3] = kv.w;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            const int qi = warp + 4 * r;                                  // warp-uniform: the q row broadcasts
+            const float* qr = qs + qi * ATT_D;
+            const float* kr = kt + lane * (ATT_D + 1);
+            float a = 0.f;
+#pragma unroll 16
+            for (int d = 0; d < ATT_D; ++d) a = fmaf(qr[d], kr[d], a);
+            sc[qi * npad + j0 + lane] = a * inv;
+        }
+    }
+    __syncthreads();
+    // ---- softmax over the n keys, two query rows per warp
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+        const int qi = warp + 4 * r;
+        float* row = sc + qi * npad;
+        float m = -INFINITY;
+        for (int j = lane; j < n; j += 32) m = fmaxf(m, row[j]);
+        m = warp_max(m);
+        float sum = 0.f;
+        for (int j = lane; j < n; j += 32) { const float e = expf(row[j] - m); row[j] = e; sum += e; }
+        sum = warp_sum(sum);
+        if (lane == 0) s_sum[qi] = sum;
+    }
+    // ---- weighted value sum: thread = (d, 4 query rows)
+    const int d = t & 63, qh = t >> 6;
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int j0 = 0; j0 < n; j0 += ATT_TK) {
+        __syncthreads();
+        for (int e = t; e < ATT_TK * ATT_D / 4; e += 128) {
+            const int jj = e >> 4, d4 = e & 15;
+            float4 vv = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (j0 + jj < n) vv = __ldg(reinterpret_cast<const float4*>(v + (long long)(j0 + jj) * C + h * ATT_D) + d4);
+            float* dst = kt + jj * (ATT_D + 1) + d4 * 4;
+            dst[0] = vv.x; dst[1] = vv.y; dst[2] = vv.z; dst[3] = vv.w;
+        }
+        __syncthreads();
+        const int jn = min(ATT_TK, n - j0);
+        for (int jj = 0; jj < jn; ++jj) {
+            const float vv = kt[jj * (ATT_D + 1) + d];
+#pragma unroll
+            for (int r = 0; r < 4; ++r) acc[r] = fmaf(sc[(qh + 2 * r) * npad + j0 + jj], vv, acc[r]);
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        const int qi = qh + 2 * r;
+        if (i0 + qi < n) out[(long long)(i0 + qi) * C + h * ATT_D + d] = acc[r] / s_sum[qi];
+    }
+}
+
 __global__ void layernorm_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
                                  const float* __restrict__ beta, float* __restrict__ out, int rows, int C, float eps) {
     const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -464,6 +550,23 @@ extern "C" int g6d_attention(const float* q, const float* k, const float* v, flo
     const size_t smem = sizeof(float) * (n + C / heads);
     attention_kernel<<<dim3(n, heads), 64, smem, as_stream(stream)>>>(q, k, v, out, n, C, heads);
     G6D_CHECK_LAUNCH("g6d_attention");
+    return G6D_OK;
+}
+
+extern "C" int g6d_attention_headmajor(const float* q, const float* k, const float* v, float* out, int n, int C, int heads,
+                                       g6d_stream_t stream) {
+    G6D_REQUIRE(q && k && v && out && n > 0 && n <= 2048 && heads > 0 && C == heads * ATT_D && (C & 3) == 0,
+                "g6d_attention_headmajor: bad args (n <= 2048, C = heads * 64)");
+    const int npad = (n + 31) & ~31;
+    const size_t smem = sizeof(float) * (ATT_TQ * ATT_D + ATT_TK * (ATT_D + 1) + (size_t)ATT_TQ * npad);
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(attention_hm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+        if (e != cudaSuccess) { set_error("g6d_attention_headmajor: %s", cudaGetErrorString(e)); return G6D_ECUDA; }
+        configured = true;
+    }
+    attention_hm_kernel<<<dim3(ceil_div(n, ATT_TQ), heads), 128, smem, as_stream(stream)>>>(q, k, v, out, n, C);
+    G6D_CHECK_LAUNCH("g6d_attention_headmajor");
     return G6D_OK;
 }
 

@@ -67,12 +67,18 @@ class ViewpointSelector(PackedModule):
         sp = self.score_process
         p['sp0'] = ops.pack_conv(sp[0].weight, sp[0].bias, pad=0, cin_pad=FEAT_PAD)
         p['sp2'] = ops.pack_conv(sp[2].weight, sp[2].bias, pad=0)
+        # attention.py:50-68 splits channels as c = d*8 + head; the tiled attention kernel wants each head's 64
+        # dims contiguous (c' = head*64 + d).  Permuting the OUTPUT rows of conv_query / conv_key / conv_feats
+        # and the INPUT columns of conv_merge once here makes the projections emit / consume that order.
+        heads, dh = 8, 64
+        hm = torch.arange(512, device=self.device)
+        hm = (hm % dh) * heads + hm // dh                     # position c' = h*64 + d  <-  reference channel d*8 + h
         p['atts'] = []
         for att in self.atts:
-            p['atts'].append({k: linear_as_conv(getattr(att, k).weight, getattr(att, k).bias)
-                              for k in ('conv_query', 'conv_key', 'conv_feats', 'conv_merge')} |
-                             {'ln_w': att.norm.norm.weight.float().contiguous(),
-                              'ln_b': att.norm.norm.bias.float().contiguous()})
+            pk = {k: linear_as_conv(getattr(att, k).weight[hm], getattr(att, k).bias[hm]) for k in ('conv_query', 'conv_key', 'conv_feats')}
+            pk['conv_merge'] = linear_as_conv(att.conv_merge.weight[:, hm], att.conv_merge.bias)
+            p['atts'].append(pk | {'ln_w': att.norm.norm.weight.float().contiguous(),
+                                   'ln_b': att.norm.norm.bias.float().contiguous()})
         p['mlps'] = [(linear_as_conv(m[0].weight, m[0].bias), linear_as_conv(m[3].weight, m[3].bias)) for m in self.mlps]
         p['score_predict'] = [linear_as_conv(self.score_predict[i].weight, self.score_predict[i].bias) for i in (0, 2)]
         # angle_predict consumes feats.permute(0,1,3,2).reshape(qn, f*an, rfn): channel = f*an + a
@@ -274,7 +280,7 @@ class ViewpointSelector(PackedModule):
             qv = ops.conv(x4, att['conv_query']).reshape(rfn, 512)
             kv = ops.conv(x4, att['conv_key']).reshape(rfn, 512)
             vv = ops.conv(x4, att['conv_feats']).reshape(rfn, 512)
-            msg = ops.attention(qv, kv, vv, heads=8)
+            msg = ops.attention(qv, kv, vv, heads=8, head_major=True)
             msg = ops.conv(msg.reshape(rfn, 1, 1, 512), att['conv_merge']).reshape(rfn, 512)
             msg = ops.layernorm(msg, att['ln_w'], att['ln_b'], 1e-5)
             y = ops.conv(torch.cat([sf, msg], 1).reshape(rfn, 1, 1, 1024), m0)

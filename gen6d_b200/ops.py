@@ -466,10 +466,12 @@ def sel_max_angle_add(x, embed):
     return out
 
 
-def attention(q, k, v, heads):
+def attention(q, k, v, heads, head_major=False):
+    """q, k, v [n, C] -> [n, C].  head_major=False: the reference's channel order c = d*heads + head;
+    True: c = head*D + d (the tiled kernel; producers / consumer permuted at pack time)."""
     n, Cc = q.shape
     out = torch.empty_like(q)
-    _call('g6d_attention', _p(q), _p(k), _p(v), _p(out), n, Cc, heads, _stream())
+    _call('g6d_attention_headmajor' if head_major else 'g6d_attention', _p(q), _p(k), _p(v), _p(out), n, Cc, heads, _stream())
     return out
 
 

@@ -260,6 +260,13 @@ int g6d_sel_max_angle_add(const float* x, const float* embed, float* out, int rf
  * q,k,v [n, C] -> out [n, C]; softmax(q_h^T k_h / sqrt(C/heads)) over keys. n <= 1024. */
 int g6d_attention(const float* q, const float* k, const float* v, float* out, int n, int C, int heads,
                   g6d_stream_t stream);
+/* The same attention over HEAD-MAJOR channels (c = head*64 + d): the layout a caller gets for free by
+ * permuting the output rows of conv_query / conv_key / conv_feats (and the input columns of conv_merge)
+ * once at pack time.  Tiled (8 queries x 1 head per block, K / V tiles staged in shared memory by coalesced
+ * loads): what the selector uses, and what keeps the replicated tail of a reference-sharded selector
+ * (n = all references over all GPUs) cheap.  n <= 2048, C = heads * 64. */
+int g6d_attention_headmajor(const float* q, const float* k, const float* v, float* out, int n, int C, int heads,
+                            g6d_stream_t stream);
 /* nn.LayerNorm(C) over the channel axis of each row (attention.py:19-26) */
 int g6d_layernorm(const float* x, const float* gamma, const float* beta, float* out, int rows, int C, float eps,
                   g6d_stream_t stream);

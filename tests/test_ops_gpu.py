@@ -184,6 +184,22 @@ def test_attention_layernorm(ops):
     close(ops.layernorm(q.cuda(), gam.cuda(), bet.cuda()), F.layer_norm(q, (Cc,), gam, bet), atol=1e-5)
 
 
+@pytest.mark.parametrize('n', [5, 64, 100, 512])
+def test_attention_head_major_tiled(ops, n):
+    """The tiled kernel on head-major channels (c = head*64 + d) equals the reference-order kernel on the
+    permuted tensors, and torch: attention.py:4-17 at n = 64 (one GPU) ... 512 (references over 8 GPUs)."""
+    Cc, heads, D = 512, 8, 64
+    q, k, v = [torch.randn(n, Cc, generator=g(80 + i)) for i in range(3)]
+    r = lambda t: t.T.reshape(1, D, heads, n)
+    scores = torch.einsum('bdhn,bdhm->bhnm', r(q), r(k)) / D ** .5
+    want = torch.einsum('bhnm,bdhm->bdhn', torch.softmax(scores, -1), r(v)).reshape(Cc, n).T        # reference channel order
+    hm = torch.arange(Cc)
+    hm = (hm % D) * heads + hm // D                          # head-major position c' <- reference channel
+    got = ops.attention(q[:, hm].contiguous().cuda(), k[:, hm].contiguous().cuda(), v[:, hm].contiguous().cuda(), heads, head_major=True)
+    close(got, want[:, hm], atol=1e-5)
+    close(got, ops.attention(q.cuda(), k.cuda(), v.cuda(), heads)[:, hm.cuda()], atol=1e-5)
+
+
 def test_linear_smallm(ops):
     x = torch.randn(3, 4096, generator=g(25)); w = torch.randn(64, 4096, generator=g(26)) * 0.02
     b = torch.randn(64, generator=g(27))

@@ -9,7 +9,9 @@ ids = db.get_img_ids()
 imgs = [db.get_image(ids[(7 + 3 * i) % len(ids)]) for i in range(8)]
 K = db.K
 N = int(sys.argv[1]) if len(sys.argv) > 1 else 48
-for workers, batch in ((6, 1), (3, 2), (2, 4), (3, 4), (4, 4), (2, 8), (3, 8), (1, 8), (1, 16)):
+import itertools
+for (workers, batch), si in itertools.product(((2, 4), (3, 4), (2, 8), (3, 8)), (5e-3, 2e-4)):
+    sys.setswitchinterval(si)
     frames = [imgs[i % len(imgs)] for i in range(N)]
     est.predict_many(frames[:workers * batch * 2], [K] * (workers * batch * 2), workers=workers, batch=batch)
     torch.cuda.synchronize()
@@ -17,4 +19,4 @@ for workers, batch in ((6, 1), (3, 2), (2, 4), (3, 4), (4, 4), (2, 8), (3, 8), (
     est.predict_many(frames, [K] * N, workers=workers, batch=batch)
     torch.cuda.synchronize()
     dt = time.perf_counter() - t0
-    print(f'workers {workers} batch {batch}: {N / dt:7.1f} poses/s ({dt / N * 1e3:.2f} ms/pose)', flush=True)
+    print(f'workers {workers} batch {batch} switchinterval {si:g}: {N / dt:7.1f} poses/s ({dt / N * 1e3:.2f} ms/pose)', flush=True)
