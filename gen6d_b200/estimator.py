@@ -221,7 +221,13 @@ class Gen6DEstimator:
                         results[i] = (poses[j], one)
                 stream.synchronize()
 
-        list(self._pool.map(run, range(workers)))
+        import sys
+        old_si = sys.getswitchinterval()
+        sys.setswitchinterval(2e-4)      # a worker that just got its D2H result should not wait 5 ms for the GIL
+        try:
+            list(self._pool.map(run, range(workers)))
+        finally:
+            sys.setswitchinterval(old_si)
         return results
 
 

@@ -10,8 +10,7 @@ imgs = [db.get_image(ids[(7 + 3 * i) % len(ids)]) for i in range(8)]
 K = db.K
 N = int(sys.argv[1]) if len(sys.argv) > 1 else 48
 import itertools
-for (workers, batch), si in itertools.product(((2, 4), (3, 4), (2, 8), (3, 8)), (5e-3, 2e-4)):
-    sys.setswitchinterval(si)
+for (workers, batch), si in itertools.product(((1, 4), (2, 4), (3, 4), (2, 8), (3, 8)), (2e-4,)):
     frames = [imgs[i % len(imgs)] for i in range(N)]
     est.predict_many(frames[:workers * batch * 2], [K] * (workers * batch * 2), workers=workers, batch=batch)
     torch.cuda.synchronize()
