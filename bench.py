@@ -590,6 +590,11 @@ def main():
     args.steps = 20 if args.steps is None else args.steps
     args.warmup = 3 if args.warmup is None else max(3, args.warmup)
     run_ours(args, rank, world, local_rank)
+    if world > 1:
+        import torch.distributed as dist
+        if dist.is_initialized():
+            dist.barrier()
+            dist.destroy_process_group()
 
 
 if __name__ == '__main__':

@@ -189,3 +189,36 @@ def test_tc_fused_output_statistics(ops, case):
     mean, var = flat.mean(1), flat.var(1, unbiased=False)
     np.testing.assert_allclose(ps.cpu().numpy(), (1 / torch.sqrt(var + 1e-5)).float().numpy(), rtol=2e-5)
     np.testing.assert_allclose(pb.cpu().numpy(), (-mean / torch.sqrt(var + 1e-5)).float().numpy(), rtol=1e-4, atol=2e-5)
+
+
+@pytest.mark.parametrize('B,hw,cin,cout', [(320, 8, 128, 128),    # 160 tiles on 148 CTAs: 19.5 K-blocks each, 12 split tiles
+                                           (320, 4, 256, 256),    # 80 tiles: every tile cut into 2-3 pieces
+                                           (150, 8, 128, 192),    # 75 x 2 tiles, the second N tile half empty
+                                           (80, 4, 256, 256),     # 20 tiles: too few for stream-K -> uniform split-K
+                                           (1, 8, 512, 512)])     # one M tile, four N tiles (uniform split-K)
+def test_tc_streamk_schedule(ops, B, hw, cin, cout):
+    """Persistent kernel with tile counts that do not divide over the grid.  Stream-K schedule (first three cases):
+    partial tiles are summed in a fixed order by the CTA that owns the tile's last K-block -- fp32-faithful,
+    bit-reproducible, and the fused InstanceNorm moments see the summed tile; the same checks on the uniform
+    split-K + reduce schedule the small cases keep."""
+    os.environ['G6D_CONV_STREAMK'] = '1'
+    x = torch.randn(B, cin, hw, hw, generator=g(70)) * 2 + 1
+    w = torch.randn(cout, cin, 3, 3, generator=g(71)) * (2 / (9 * cin)) ** .5
+    b = torch.randn(cout, generator=g(72))
+    xn = F.relu(F.instance_norm(x.double()))
+    ref = F.conv2d(xn, w.double(), b.double(), padding=1).float()
+    xc = nhwc(x)
+    ps, pb = ops.instnorm_stats(xc, rows_per_group=hw * hw)
+    pc = ops.pack_conv(w.cuda(), b.cuda(), pad=1)
+    rows = hw * hw if (hw * hw) % 32 == 0 else 32
+    kw = dict(prologue=ops.PRO_AFFINE_RELU, pro_scale=ps, pro_shift=pb, group_rows=1)
+    if (B * hw * hw) % rows == 0:
+        y, ws = ops.conv(xc, pc, stats_rows=rows, **kw)
+        want = ops.instnorm_partial(y, rows_per_group=rows)
+        np.testing.assert_allclose(ws.cpu().numpy(), want.cpu().numpy(), rtol=2e-6, atol=1e-4)
+    else:
+        y = ops.conv(xc, pc, **kw)
+    assert rel_err(nchw(y), ref) < 2e-5
+    y2 = ops.conv(xc, pc, **kw)
+    os.environ.pop('G6D_CONV_STREAMK', None)
+    assert torch.equal(y, y2)
