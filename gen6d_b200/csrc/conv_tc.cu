@@ -82,9 +82,6 @@ struct ConvTcP {
     long long group_rows;
     int M, K, kblocks, splits, kb_per_split;
     double* stats; long long stats_rows;      // fused InstanceNorm statistics of the OUTPUT (see epilogue_stats)
-    // stream-K (see Tc2Iter): the tiles x K-blocks unit space is cut into sk_grid equal contiguous ranges
-    int sk, sk_grid, sk_units;
-    unsigned* sk_flags; float* sk_ws;
 };
 
 // ------------------------------------------------------------------------------------------ operand split
@@ -231,71 +228,6 @@ template <int BN> struct Tc2Cfg {
 
 struct Tc2Work { int m_tiles, n_tiles, total; };
 
-// Work items of one persistent CTA.  Two schedules:
-//   * tile schedule: item w = blockIdx.x + i * gridDim.x -> (M tile, N tile, uniform K split); with splits > 1 every
-//     item writes a partial slab and a reduce kernel follows (mode 3; kept for the accuracy-mandated splits of long K);
-//   * stream-K schedule (p.sk): the unit space [0, tiles * kblocks) -- tile-major, K-block minor -- is cut into
-//     gridDim.x equal contiguous ranges, so every CTA runs the same number of K-blocks whatever the tile count
-//     (80 or 160 tiles on 148 SMs used to cost one or two full rounds: 54 % of the machine; fill_tc_params picks the
-//     schedule).  A range is walked from
-//     its TOP end down: the piece that does not reach its tile's last K-block (mode 1, at most one per CTA, always
-//     the first item) is stored as fp32 partial sums in slab[blockIdx.x] and published through sk_flags[blockIdx.x];
-//     the CTA that owns a tile's last K-block (mode 2, always ITS last item) adds the slabs of the CTAs below it in
-//     ascending order -- a fixed order, so results are deterministic -- and runs the normal epilogue.  Producers of a
-//     partial publish it at the START of their run and consumers need it at the END of theirs: the wait is free
-//     unless the grid is not co-resident, and then lower-numbered CTAs (which never wait on higher ones) still drain.
-struct Tc2Item { int mt, nt, sp, kb_begin, nkb, mode; };
-struct Tc2Iter { int w, u_lo, u_hi; };
-__device__ __forceinline__ int sk_bound(const ConvTcP& p, int c) { return (int)((long long)c * p.sk_units / p.sk_grid); }
-// owner of unit u: the largest c with sk_bound(c) <= u
-__device__ __forceinline__ int sk_owner(const ConvTcP& p, int u) { return (int)((((long long)u + 1) * p.sk_grid - 1) / p.sk_units); }
-__device__ __forceinline__ void tc2_iter_init(Tc2Iter& it, const ConvTcP& p) {
-    it.w = blockIdx.x; it.u_lo = 0; it.u_hi = 0;
-    if (p.sk) { it.u_lo = sk_bound(p, blockIdx.x); it.u_hi = sk_bound(p, blockIdx.x + 1); }
-}
-__device__ __forceinline__ bool tc2_iter_next(Tc2Iter& it, const ConvTcP& p, const Tc2Work& wk, Tc2Item& o) {
-    if (!p.sk) {
-        if (it.w >= wk.total) return false;
-        int w = it.w; it.w += gridDim.x;
-        // n fastest so neighbouring CTAs share the gathered A rows in L2
-        o.nt = w % wk.n_tiles; w /= wk.n_tiles;
-        o.mt = w % wk.m_tiles;
-        o.sp = w / wk.m_tiles;
-        o.kb_begin = o.sp * p.kb_per_split;
-        o.nkb = min(p.kblocks, o.kb_begin + p.kb_per_split) - o.kb_begin;
-        o.mode = p.splits > 1 ? 3 : 0;
-        return true;
-    }
-    if (it.u_hi <= it.u_lo) return false;
-    const int t = (it.u_hi - 1) / p.kblocks;
-    const int t0 = t * p.kblocks;
-    const int lo = it.u_lo > t0 ? it.u_lo : t0;
-    o.kb_begin = lo - t0; o.nkb = it.u_hi - lo;
-    o.mode = it.u_hi == t0 + p.kblocks ? (o.kb_begin == 0 ? 0 : 2) : 1;
-    o.nt = t % wk.n_tiles; o.mt = t / wk.n_tiles; o.sp = 0;
-    it.u_hi = lo;
-    return true;
-}
-// bounded acquire-spin on a stream-K flag (same bail-out contract as mbar_wait)
-__device__ __forceinline__ void sk_wait_flag(const unsigned* flag, unsigned want, int who, int iter) {
-    const long long t0 = clock64();
-    unsigned spins = 0;
-    for (;;) {
-        unsigned v;
-        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
-        if (v >= want) return;
-        if ((++spins & 15u) != 0) continue;
-        if (*(volatile int*)&g_tc_timeout[0] != 0) return;
-        if (clock64() - t0 > 500000000ll) {
-            if (atomicCAS(&g_tc_timeout[0], 0, 1) == 0) {
-                g_tc_timeout[1] = who; g_tc_timeout[2] = iter; g_tc_timeout[3] = (int)v;
-                g_tc_timeout[4] = (int)blockIdx.x; g_tc_timeout[5] = 0; g_tc_timeout[6] = 0; g_tc_timeout[7] = (int)threadIdx.x;
-            }
-            return;
-        }
-    }
-}
-
 template <int BN, int KIND, int NPW>
 __global__ void __launch_bounds__(tc2_threads(NPW), 1)  // 448 threads x 128 registers, or 704 x 80 (warps allocate registers in units of 512)
 conv_tc2_kernel(const ConvTcP p, const Tc2Work wk, const __grid_constant__ CUtensorMap map_hi,
@@ -347,6 +279,13 @@ conv_tc2_kernel(const ConvTcP p, const Tc2Work wk, const __grid_constant__ CUten
     tc_fence_after();
     const uint32_t tmem_acc = *tmem_slot;
 
+    // work item -> (m tile, n tile, split); n fastest so neighbouring CTAs share the gathered A rows in L2
+    auto decode = [&](int w, int& mt, int& nt, int& sp) {
+        nt = w % wk.n_tiles; w /= wk.n_tiles;
+        mt = w % wk.m_tiles;
+        sp = w / wk.m_tiles;
+    };
+
     if (warp < NPW) {
         // =============================== A producers ===============================
         // All producer warps fill every K-block: ROWS rows x one 16-byte smem chunk (4 or 8 channels) per thread.
@@ -354,12 +293,12 @@ conv_tc2_kernel(const ConvTcP p, const Tc2Work wk, const __grid_constant__ CUten
         const int cofs = chunk * 4;                        // this thread's channels inside the K-block: [cofs, cofs+4) (+32 for the 2nd load)
         const int r0 = threadIdx.x >> 3;                   // rows r0 + RSTEP*j, j < ROWS
         int git = 0;                                       // global K-block counter of this CTA
-        Tc2Iter iter; Tc2Item itm;
-        tc2_iter_init(iter, p);
-        while (tc2_iter_next(iter, p, wk, itm)) {
-            const int m_base = itm.mt * TC_BM;
-            const int kb_begin = itm.kb_begin;
-            const int nkb = itm.nkb;
+        for (int w = blockIdx.x; w < wk.total; w += gridDim.x) {
+            int mt, nt, sp;
+            decode(w, mt, nt, sp);
+            const int m_base = mt * TC_BM;
+            const int kb_begin = sp * p.kb_per_split;
+            const int nkb = min(p.kblocks, kb_begin + p.kb_per_split) - kb_begin;
             int rb[ROWS], rsp[ROWS], rc[ROWS];
             unsigned rvmask = 0;
             const long long plane_sz = (long long)p.D * p.H * p.W;
@@ -461,12 +400,11 @@ conv_tc2_kernel(const ConvTcP p, const Tc2Work wk, const __grid_constant__ CUten
         // =============================== B producer (TMA) ===============================
         if (lane == 0) {
             int git = 0;
-            Tc2Iter iter; Tc2Item itm;
-            tc2_iter_init(iter, p);
-            while (tc2_iter_next(iter, p, wk, itm)) {
-                const int nt = itm.nt;
-                const int kb_begin = itm.kb_begin;
-                const int nkb = itm.nkb;
+            for (int w = blockIdx.x; w < wk.total; w += gridDim.x) {
+                int mt, nt, sp;
+                decode(w, mt, nt, sp);
+                const int kb_begin = sp * p.kb_per_split;
+                const int nkb = min(p.kblocks, kb_begin + p.kb_per_split) - kb_begin;
                 // The weight tiles of a small-M layer are touched once and come from HBM: with only
                 // STAGES tiles in flight the ring is latency-bound (measured 5000 cycles per K-block
                 // at M = 660).  An L2 prefetch running PF K-blocks ahead costs no shared memory.
@@ -493,10 +431,11 @@ conv_tc2_kernel(const ConvTcP p, const Tc2Work wk, const __grid_constant__ CUten
         if (elect_one_sync()) {
             const uint32_t idesc = umma_idesc<KIND>(TC_BM, BN);
             int git = 0, tile = 0;
-            Tc2Iter iter; Tc2Item itm;
-            tc2_iter_init(iter, p);
-            for (; tc2_iter_next(iter, p, wk, itm); ++tile) {
-                const int nkb = itm.nkb;
+            for (int w = blockIdx.x; w < wk.total; w += gridDim.x, ++tile) {
+                int mt, nt, sp;
+                decode(w, mt, nt, sp);
+                const int kb_begin = sp * p.kb_per_split;
+                const int nkb = min(p.kblocks, kb_begin + p.kb_per_split) - kb_begin;
                 const int buf = tile & 1;
                 mbar_wait(tmem_empty(buf), ((tile >> 1) & 1) ^ 1, 6, tile);     // epilogue has drained this buffer
                 tc_fence_after();
@@ -539,34 +478,24 @@ conv_tc2_kernel(const ConvTcP p, const Tc2Work wk, const __grid_constant__ CUten
     } else {
         // =============================== epilogue (the 4 warps after the MMA warp) ===============================
         const int quad = warp & 3;                     // TMEM lane quadrant = warp id % 4
-        const int row = quad * 32 + lane;              // tile row of this thread
         int tile = 0;
-        Tc2Iter iter; Tc2Item itm;
-        tc2_iter_init(iter, p);
-        for (; tc2_iter_next(iter, p, wk, itm); ++tile) {
-            const int mt = itm.mt, nkb = itm.nkb;
+        for (int w = blockIdx.x; w < wk.total; w += gridDim.x, ++tile) {
+            int mt, nt, sp;
+            decode(w, mt, nt, sp);
+            const int kb_begin = sp * p.kb_per_split;
+            const int nkb = min(p.kblocks, kb_begin + p.kb_per_split) - kb_begin;
             const int buf = tile & 1;
             mbar_wait(tmem_full(buf), (tile >> 1) & 1, 2, tile);
             tc_fence_after();
-            const int m = mt * TC_BM + row;
-            const int n_base = itm.nt * BN;
-            const bool partial = itm.mode == 3;            // uniform split-K slab, reduced by a second kernel
-            const bool sk_part = itm.mode == 1;            // stream-K partial: slab[blockIdx.x]
+            const int m = mt * TC_BM + quad * 32 + lane;
+            const int n_base = nt * BN;
+            const bool partial = p.splits > 1;
             // 128-bit stores need 16-byte aligned rows: channel strides / offsets multiples of 4 floats
             const bool vec_ok = partial ? (p.Cout & 3) == 0
                                         : ((p.ocs & 3) == 0 && (p.oco & 3) == 0 && (reinterpret_cast<uintptr_t>(p.y) & 15) == 0 &&
                                            (!p.bias || (reinterpret_cast<uintptr_t>(p.bias) & 15) == 0));
             const int n_acc = nkb < NMAIN ? nkb : NMAIN;
             const uint32_t tbase = tmem_acc + (uint32_t)(buf * Cfg::BUF_COLS) + ((uint32_t)(quad * 32) << 16);
-            // stream-K slabs: [16-column chunk][tile row][16] floats, 64 contiguous bytes per thread and chunk
-            float* const my_slab = p.sk_ws + (long long)blockIdx.x * (TC_BM * BN) + row * 16;
-            int sk_first = blockIdx.x;
-            if (itm.mode == 2) {
-                // the CTAs below this one that hold the other pieces of the tile; their partials were the first
-                // thing they produced (all four epilogue warps of a CTA count into its flag)
-                sk_first = sk_owner(p, (itm.mt * wk.n_tiles + itm.nt) * p.kblocks);
-                for (int cp = sk_first; cp < (int)blockIdx.x; ++cp) sk_wait_flag(p.sk_flags + cp, 4u, 7, cp);
-            }
 #pragma unroll 1
             for (int cc = 0; cc < BN; cc += 16) {
                 float accv[16];
@@ -585,22 +514,6 @@ conv_tc2_kernel(const ConvTcP p, const Tc2Work wk, const __grid_constant__ CUten
                         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
                         for (int j = 0; j < 16; ++j) accv[j] += __uint_as_float(r[j]);
-                    }
-                }
-                if (sk_part) {
-                    float4* dst = reinterpret_cast<float4*>(my_slab + (cc >> 4) * (TC_BM * 16));
-#pragma unroll
-                    for (int j4 = 0; j4 < 4; ++j4)
-                        dst[j4] = make_float4(accv[j4 * 4], accv[j4 * 4 + 1], accv[j4 * 4 + 2], accv[j4 * 4 + 3]);
-                    continue;
-                }
-                for (int cp = sk_first; cp < (int)blockIdx.x; ++cp) {      // mode 2 only: the pieces below, ascending
-                    const float4* src = reinterpret_cast<const float4*>(p.sk_ws + (long long)cp * (TC_BM * BN) + row * 16 +
-                                                                        (cc >> 4) * (TC_BM * 16));
-#pragma unroll
-                    for (int j4 = 0; j4 < 4; ++j4) {
-                        const float4 pv = __ldcg(src + j4);                // L2: written by another SM during this launch
-                        accv[j4 * 4] += pv.x; accv[j4 * 4 + 1] += pv.y; accv[j4 * 4 + 2] += pv.z; accv[j4 * 4 + 3] += pv.w;
                     }
                 }
                 const int n0 = n_base + cc;
@@ -624,7 +537,7 @@ conv_tc2_kernel(const ConvTcP p, const Tc2Work wk, const __grid_constant__ CUten
                     }
                 }
                 if (m < p.M) {
-                    float* dst = partial ? p.ws + ((long long)itm.sp * p.M + m) * p.Cout + n0
+                    float* dst = partial ? p.ws + ((long long)sp * p.M + m) * p.Cout + n0
                                          : p.y + (long long)m * p.ocs + p.oco + n0;
                     if (vec_ok && n0 + 16 <= p.Cout) {      // 4 x 128-bit stores per thread instead of 16 scalar ones
 #pragma unroll
@@ -638,11 +551,6 @@ conv_tc2_kernel(const ConvTcP p, const Tc2Work wk, const __grid_constant__ CUten
                 }
                 if (p.stats && !partial)
                     epilogue_stats(accv, m < p.M, p.stats, (long long)(mt * TC_BM + quad * 32) / p.stats_rows, p.Cout, n0, lane);
-            }
-            if (sk_part) {
-                __threadfence();                           // every lane: its slab stores before the flag
-                __syncwarp();
-                if (lane == 0) atomicAdd(p.sk_flags + blockIdx.x, 1u);
             }
             tc_fence_before();
             __syncwarp();
@@ -762,15 +670,6 @@ static bool tc2_dims_ok(const g6d_conv_desc* d) {
            (long long)d->D * d->H * d->W < (1ll << 30) && d->group_rows < (1ll << 31);
 }
 
-// G6D_CONV_STREAMK=1 opts in to the stream-K schedule.  Off by default: measured on B200, single layers gain
-// x1.13-1.65 (tools/streamk_ab.py) but the pose step LOSES 5 % (164 -> 155 poses/s, single-frame latency 10.4 ->
-// 10.6 ms): the selector's three scale towers already run on concurrent branch streams, so the SMs a short grid
-// leaves idle were being used by the neighbouring tower, and whole-machine grids with extra epilogues only add work.
-static bool streamk_enabled() {
-    const char* e = getenv("G6D_CONV_STREAMK");      // read per call: the A/B tool flips it inside one process
-    return e && e[0] == '1';
-}
-
 static int fill_tc_params(const g6d_conv_desc* d, int kind, ConvTcP& p) {
     G6D_REQUIRE(d != nullptr, "g6d_conv_tc: null desc");
     G6D_REQUIRE(kind == G6D_TC_TF32 || kind == G6D_TC_F16, "g6d_conv_tc: bad operand kind %d", kind);
@@ -798,6 +697,14 @@ static int fill_tc_params(const g6d_conv_desc* d, int kind, ConvTcP& p) {
     const int bn = tc_block_n(d->Cout);
     const long long ctas = (long long)ceil_div(M, TC_BM) * ceil_div(d->Cout, bn);
     const int min_kb = 256 / bk;                     // never split below 256 K-elements per item
+    int splits = 1;
+    if (ctas < kNumSMs && p.kblocks >= 2 * min_kb) {
+        // as many K splits as still fit in ONE wave of the 148 persistent CTAs (a second, partial wave
+        // of long items costs more than the parallelism it adds)
+        splits = (int)(kNumSMs / ctas);
+        splits = splits > p.kblocks / min_kb ? p.kblocks / min_kb : splits;
+        splits = splits < 1 ? 1 : splits;
+    }
     // The tensor core adds each K-step into the fp32 accumulator with truncation; over very long
     // K chains of same-sign products (detector correlation: K = 115200 of post-ReLU features)
     // that is a systematic bias of ~4e-5 relative.  For long-K problems (K > 8192) the chain per
@@ -807,43 +714,11 @@ static int fill_tc_params(const g6d_conv_desc* d, int kind, ConvTcP& p) {
     const int chain = d->max_chain_k > 0 ? d->max_chain_k * nmain : (K > 8192 ? TC_MAX_K_PER_CHAIN : 0);
     const int max_kb = chain > bk ? chain / bk : 1;
     const int min_splits = chain > 0 ? (p.kblocks + max_kb - 1) / max_kb : 1;
-    p.sk = 0; p.sk_grid = 0; p.sk_units = 0;
-    if (min_splits == 1 && streamk_enabled() && ctas < 8 * kNumSMs && ctas * p.kblocks < (1ll << 30)) {
-        // stream-K: equal K-block counts per CTA.  Not worth it when the tiles already divide evenly over the
-        // grid, or when there are so many rounds that the last, partial one is noise.
-        const long long units = ctas * p.kblocks;
-        long long grid = units / min_kb;
-        grid = grid > kNumSMs ? kNumSMs : (grid < 1 ? 1 : grid);
-        // Measured on B200 (tools/streamk_ab.py): x1.13-1.65 on the selector's 80- / 160- / 320-tile layers, but a
-        // tile cut into many pieces loses to uniform split-K + the machine-wide reduce kernel (the one finishing CTA
-        // reads every slab: x0.3-0.56 at 4-12 tiles), and ranges shorter than ~768 K-elements only pay the extra
-        // epilogues (x0.95).  So: at most three pieces per tile, at least 768 K-elements per CTA.
-        const long long per_cta = units / grid;
-        if (ctas % grid != 0 && 2 * per_cta >= p.kblocks && per_cta * bk >= 768) {
-            p.sk = 1; p.sk_grid = (int)grid; p.sk_units = (int)units;
-            p.splits = 1; p.kb_per_split = p.kblocks;
-            return G6D_OK;
-        }
-    }
-    int splits = 1;
-    if (ctas < kNumSMs && p.kblocks >= 2 * min_kb) {
-        // as many K splits as still fit in ONE wave of the 148 persistent CTAs (a second, partial wave
-        // of long items costs more than the parallelism it adds)
-        splits = (int)(kNumSMs / ctas);
-        splits = splits > p.kblocks / min_kb ? p.kblocks / min_kb : splits;
-        splits = splits < 1 ? 1 : splits;
-    }
     splits = splits < min_splits ? min_splits : splits;
     splits = splits > 64 ? 64 : splits;
     p.kb_per_split = (p.kblocks + splits - 1) / splits;
     p.splits = (p.kblocks + p.kb_per_split - 1) / p.kb_per_split;
     return G6D_OK;
-}
-
-constexpr int SK_FLAG_BYTES = 1024;                  // kNumSMs flags in front of the stream-K slabs
-static long long tc2_workspace_bytes(const ConvTcP& p) {
-    if (p.sk) return SK_FLAG_BYTES + (long long)p.sk_grid * TC_BM * tc_block_n(p.Cout) * (long long)sizeof(float);
-    return p.splits > 1 ? (long long)p.splits * p.M * p.Cout * (long long)sizeof(float) : 0;
 }
 
 template <int BN, int KIND, int NPW = 8>
@@ -859,11 +734,7 @@ static int launch_tc2(const ConvTcP& p, const CUtensorMap& mh, const CUtensorMap
     wk.m_tiles = ceil_div(p.M, TC_BM); wk.n_tiles = ceil_div(p.Cout, BN);
     const long long total = (long long)wk.m_tiles * wk.n_tiles * p.splits;
     wk.total = (int)total;
-    const int grid = p.sk ? p.sk_grid : (total < kNumSMs ? (int)total : kNumSMs);
-    if (p.sk) {
-        cudaError_t e = cudaMemsetAsync(p.sk_flags, 0, SK_FLAG_BYTES, st);
-        if (e != cudaSuccess) { set_error("g6d_conv_tc: memset: %s", cudaGetErrorString(e)); return G6D_ECUDA; }
-    }
+    const int grid = total < kNumSMs ? (int)total : kNumSMs;
     conv_tc2_kernel<BN, KIND, NPW><<<grid, tc2_threads(NPW), Cfg::SMEM_BYTES, st>>>(p, wk, mh, ml);
     G6D_CHECK_LAUNCH("g6d_conv_tc");
     return G6D_OK;
@@ -1363,7 +1234,7 @@ extern "C" long long g6d_conv_tc_workspace_bytes(const g6d_conv_desc* desc, int 
     }
     ConvTcP p{};
     if (fill_tc_params(desc, kind, p) != G6D_OK) return -1;
-    return tc2_workspace_bytes(p);
+    return p.splits > 1 ? (long long)p.splits * p.M * p.Cout * (long long)sizeof(float) : 0;
 }
 
 // fused output statistics are possible when every 32-row epilogue slice lies in one group
@@ -1425,9 +1296,7 @@ extern "C" int g6d_conv_tc(const g6d_conv_desc* desc, const float* x, const void
     G6D_REQUIRE(w_rows >= p.Cout, "g6d_conv_tc: weight rows (%d) < Cout (%d)", w_rows, p.Cout);
     if (p.pro != G6D_PRO_NONE) G6D_REQUIRE(pro_scale && pro_shift, "g6d_conv_tc: prologue operands missing");
     if (p.splits > 1) G6D_REQUIRE(ws != nullptr, "g6d_conv_tc: split-K workspace required (%d splits)", p.splits);
-    if (p.sk) G6D_REQUIRE(ws != nullptr && (reinterpret_cast<uintptr_t>(ws) & 15) == 0, "g6d_conv_tc: stream-K workspace required (16-byte aligned)");
     p.x = x; p.bias = bias; p.ps = pro_scale; p.pb = pro_shift; p.y = y; p.ws = (float*)ws;
-    p.sk_flags = (unsigned*)ws; p.sk_ws = (float*)ws + SK_FLAG_BYTES / 4;
     p.stats = stats; p.stats_rows = stats ? stats_rows : 1;
     const int bn = tc_block_n(p.Cout);
     CUtensorMap mh, ml;

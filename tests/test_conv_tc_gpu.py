@@ -191,17 +191,15 @@ def test_tc_fused_output_statistics(ops, case):
     np.testing.assert_allclose(pb.cpu().numpy(), (-mean / torch.sqrt(var + 1e-5)).float().numpy(), rtol=1e-4, atol=2e-5)
 
 
-@pytest.mark.parametrize('B,hw,cin,cout', [(320, 8, 128, 128),    # 160 tiles on 148 CTAs: 19.5 K-blocks each, 12 split tiles
-                                           (320, 4, 256, 256),    # 80 tiles: every tile cut into 2-3 pieces
+@pytest.mark.parametrize('B,hw,cin,cout', [(320, 8, 128, 128),    # 160 tiles on 148 CTAs
+                                           (320, 4, 256, 256),    # 80 tiles
                                            (150, 8, 128, 192),    # 75 x 2 tiles, the second N tile half empty
-                                           (80, 4, 256, 256),     # 20 tiles: too few for stream-K -> uniform split-K
+                                           (80, 4, 256, 256),     # 20 tiles -> uniform split-K
                                            (1, 8, 512, 512)])     # one M tile, four N tiles (uniform split-K)
-def test_tc_streamk_schedule(ops, B, hw, cin, cout):
-    """Persistent kernel with tile counts that do not divide over the grid.  Stream-K schedule (first three cases):
-    partial tiles are summed in a fixed order by the CTA that owns the tile's last K-block -- fp32-faithful,
-    bit-reproducible, and the fused InstanceNorm moments see the summed tile; the same checks on the uniform
-    split-K + reduce schedule the small cases keep."""
-    os.environ['G6D_CONV_STREAMK'] = '1'
+def test_tc_tile_counts_that_do_not_divide_the_grid(ops, B, hw, cin, cout):
+    """Persistent kernel with tile counts that do not divide over its 148 CTAs (a partial last round, or a short
+    grid with uniform split-K + the reduce kernel), InstanceNorm prologue and fused output moments: fp32-faithful
+    and bit-reproducible."""
     x = torch.randn(B, cin, hw, hw, generator=g(70)) * 2 + 1
     w = torch.randn(cout, cin, 3, 3, generator=g(71)) * (2 / (9 * cin)) ** .5
     b = torch.randn(cout, generator=g(72))
@@ -220,5 +218,4 @@ def test_tc_streamk_schedule(ops, B, hw, cin, cout):
         y = ops.conv(xc, pc, **kw)
     assert rel_err(nchw(y), ref) < 2e-5
     y2 = ops.conv(xc, pc, **kw)
-    os.environ.pop('G6D_CONV_STREAMK', None)
     assert torch.equal(y, y2)
