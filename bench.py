@@ -33,7 +33,24 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 E2E_WORKERS = int(os.environ.get('G6D_E2E_WORKERS', '2'))      # host threads / CUDA streams per GPU (predict_many / device lanes)
-E2E_BATCH = int(os.environ.get('G6D_E2E_BATCH', '4'))          # frames per batched stage (predict_batch); WORKERS x BATCH frames in flight
+E2E_BATCH = int(os.environ.get('G6D_E2E_BATCH', '0'))          # frames per batched stage (predict_batch); 0 = pick_batch(steps)
+E2E_MAX_BATCH = 10
+
+
+def pick_batch(steps, workers):
+    """Frames per batched stage for a timed region of `steps` poses on `workers` lanes: the largest batch <= 10 that
+    deals every lane the same number of full batches (steps 20, 2 lanes -> 10; a ragged tail would leave one lane
+    idle for a whole batch), 4 when nothing divides.  Measured on B200 at 20 steps (2 lanes): batch 4 -> 164 poses/s
+    device-resident / 123-135 end to end, 5 -> 172 / 130, 10 -> 171-174 / 138-142; 1 lane x 20 -> 162 / 139;
+    4 lanes x 5 -> 171 / 135."""
+    if E2E_BATCH > 0:
+        return E2E_BATCH
+    if steps % workers == 0:
+        per_lane = steps // workers
+        for b in range(min(E2E_MAX_BATCH, per_lane), 3, -1):
+            if per_lane % b == 0:
+                return b
+    return 4
 METRIC = 'poses/sec end-to-end (128^2 crop, 64 refs, 3 refine iters)'
 WORKLOAD = ('full estimator detect->select->3x refine: synthetic 480x640 frame, detector 32 refs x 4 scales, '
             'selector 64 refs x 5 angles, refiner 6 views 32^3 volume, seeded random weights')
@@ -345,7 +362,7 @@ def run_ours(args, rank, world, local_rank):
     # recorded with its device-resident inputs and replayed -- exactly what predict_batch launches, minus
     # host geometry and copies.  W lanes (clones with private graphs, shared weights / reference features),
     # each on its own stream, keep W x B frames in flight.
-    W, Bt = E2E_WORKERS, E2E_BATCH
+    W, Bt = E2E_WORKERS, pick_batch(args.steps, E2E_WORKERS)
     batch_imgs = [db.get_image(frames[i % len(frames)]) for i in range(Bt)]
 
     def record(e):
@@ -448,11 +465,11 @@ def run_ours(args, rank, world, local_rank):
     note('single-frame e2e done')
     # the throughput API: W host threads x batches of Bt frames through predict_batch
     def pipelined(n):
-        res = est.predict_many([imgs[i % len(imgs)] for i in range(n)], [K] * n, workers=E2E_WORKERS, batch=E2E_BATCH)
+        res = est.predict_many([imgs[i % len(imgs)] for i in range(n)], [K] * n, workers=E2E_WORKERS, batch=Bt)
         out_poses.extend(r[0] for r in res)
 
-    pipelined(2 * E2E_WORKERS * E2E_BATCH)             # builds the worker clones, captures their graphs
-    pipelined(max(args.warmup, E2E_WORKERS * E2E_BATCH))   # untimed warm-up of the whole pipelined path
+    pipelined(2 * E2E_WORKERS * Bt)             # builds the worker clones, captures their graphs
+    pipelined(max(args.warmup, E2E_WORKERS * Bt))   # untimed warm-up of the whole pipelined path
     barrier()
     t0 = time.perf_counter()
     pipelined(args.steps)
@@ -535,13 +552,13 @@ def run_ours(args, rank, world, local_rank):
             'warmup': args.warmup, 'ms_per_step': dev_ms / args.steps, 'higher_is_better': True, 'scaling': 'weak',
             'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
             'config': {'workload': WORKLOAD, 'parallelism': f'replica x{world} (independent frames per GPU); per GPU {E2E_WORKERS} lanes (streams) x batches of '
-                                                            f'{E2E_BATCH} frames through the batched stages = {E2E_WORKERS * E2E_BATCH} frames in flight',
+                                                            f'{Bt} frames through the batched stages = {E2E_WORKERS * Bt} frames in flight',
                        'l2': 'per-step working set (220 MB selector reference stack + 300 MB weights + detector '
                              'activations) exceeds the 126 MB L2; no explicit flush'},
             'e2e': {'value': world * args.steps / (pipe_ms * 1e-3), 'unit': 'poses/s', 'ms_per_step': pipe_ms / args.steps,
                     'h2d_bytes_per_step': io['h2d'] // n_calls, 'd2h_bytes_per_step': io['d2h'] // n_calls,
-                    'api': f'Gen6DEstimator.predict_many(numpy frames, Ks, workers={E2E_WORKERS}, batch={E2E_BATCH}) -> numpy poses: {E2E_WORKERS} host threads '
-                           f'each push batches of {E2E_BATCH} frames through predict_batch (pinned H2D of the frames once, crops cut from them on the device, '
+                    'api': f'Gen6DEstimator.predict_many(numpy frames, Ks, workers={E2E_WORKERS}, batch={Bt}) -> numpy poses: {E2E_WORKERS} host threads '
+                           f'each push batches of {Bt} frames through predict_batch (pinned H2D of the frames once, crops cut from them on the device, '
                            'camera geometry on the host, one D2H per stage and batch)',
                     'single_frame_latency': {'value': e2e_v, 'unit': 'poses/s', 'ms_per_step': e2e_wall_ms / args.steps,
                                              'api': 'Gen6DEstimator.predict(numpy frame, K), one frame at a time'}},

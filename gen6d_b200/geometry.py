@@ -180,14 +180,23 @@ def affine_dst_to_src(M):
     return np.asarray(m + [0.0, 0.0, 1.0])
 
 
+def warp_source(t):
+    """(device pointer, rows, cols) of a contiguous CUDA uint8 [rows, cols, 3] tensor: the source half of a
+    g6d_warp_job.  Long-lived sources (the resident database images) are described once and reused."""
+    if t.dim() != 3 or t.shape[2] != 3 or not t.is_contiguous() or not t.is_cuda or t.element_size() != 1:
+        raise ValueError('pack_warp_jobs: sources must be contiguous CUDA uint8 [rows, cols, 3] tensors')
+    return (t.data_ptr(), t.shape[0], t.shape[1])
+
+
 def pack_warp_jobs(srcs, mats):
-    """srcs: device uint8 tensors [rows, cols, 3] (contiguous); mats: dst->src matrices [9].
-    -> uint8 [n*88] host array, the g6d_warp_job records of include/gen6d_b200.h."""
-    jobs = np.zeros(len(srcs), WARP_JOB)
-    for j, (t, m) in enumerate(zip(srcs, mats)):
-        if t.dim() != 3 or t.shape[2] != 3 or not t.is_contiguous() or not t.is_cuda or t.element_size() != 1:
-            raise ValueError('pack_warp_jobs: sources must be contiguous CUDA uint8 [rows, cols, 3] tensors')
-        jobs[j] = (t.data_ptr(), t.shape[0], t.shape[1], m)
+    """srcs: device uint8 tensors [rows, cols, 3] (contiguous) or their warp_source() triples; mats: dst->src
+    matrices [9].  -> uint8 [n*88] host array, the g6d_warp_job records of include/gen6d_b200.h."""
+    desc = [s if isinstance(s, tuple) else warp_source(s) for s in srcs]
+    jobs = np.zeros(len(desc), WARP_JOB)
+    if desc:
+        ptr, rows, cols = zip(*desc)
+        jobs['src'], jobs['rows'], jobs['cols'] = ptr, rows, cols
+        jobs['M'] = np.asarray(mats, np.float64).reshape(len(desc), 9)
     return jobs.view(np.uint8)
 
 
@@ -239,10 +248,13 @@ def _look_at_batch(cen_px, Ks):
     xy = c / f[:, None]
     a, b = -np.arctan2(xy[:, 0], 1.0), np.arctan2(xy[:, 1], 1.0)
     ca, sa, cb, sb = np.cos(a), np.sin(a), np.cos(b), np.sin(b)
-    z, o = np.zeros_like(a), np.ones_like(a)
-    ry = np.stack([np.stack([ca, z, sa], -1), np.stack([z, o, z], -1), np.stack([-sa, z, ca], -1)], 1)
-    rx = np.stack([np.stack([o, z, z], -1), np.stack([z, cb, -sb], -1), np.stack([z, sb, cb], -1)], 1)
-    return rx @ ry, np.sqrt(np.sum(c * c, 1) + f * f)
+    # rx @ ry written out (every element is a single product: no rounding difference to the matrix product,
+    # and no np.stack calls -- they were a third of refine_problem's time)
+    R = np.zeros((len(a), 3, 3))
+    R[:, 0, 0], R[:, 0, 2] = ca, sa
+    R[:, 1, 0], R[:, 1, 1], R[:, 1, 2] = sb * sa, cb, -(sb * ca)
+    R[:, 2, 0], R[:, 2, 1], R[:, 2, 2] = -(cb * sa), sb, cb * ca
+    return R, np.sqrt(np.sum(c * c, 1) + f * f)
 
 
 def _project_center_batch(center, poses, Ks):
@@ -271,6 +283,23 @@ def reference_view_table(database, ids, size, margin):
             'Kinv': np.linalg.inv(Ks)}
 
 
+def _views_at_angle(tab, angle, size):
+    """Second half of normalize_reference_views for table rows `tab` [n] and in-plane angles [n]:
+    (K_new [n,3,3] f32, poses_new [n,3,4], Hs [n,3,3] f64).  Every view is independent of the others."""
+    poses, n = tab['poses'], len(angle)
+    ca, sa = np.cos(angle), np.sin(angle)
+    Rz = np.zeros((n, 3, 3), np.float32)                       # reference builds R_z in float32
+    Rz[:, 0, 0], Rz[:, 0, 1], Rz[:, 1, 0], Rz[:, 1, 1], Rz[:, 2, 2] = ca, -sa, sa, ca, 1
+    R = Rz @ tab['R_look']
+    K_new = np.zeros((n, 3, 3), np.float32)
+    K_new[:, 0, 0] = K_new[:, 1, 1] = tab['f']
+    K_new[:, 0, 2], K_new[:, 1, 2], K_new[:, 2, 2] = size / 2, size / 2, 1
+    Hs = K_new @ R @ tab['Kinv']
+    rect = R.astype(np.float32)
+    poses_new = np.concatenate([rect @ poses[:, :, :3], rect @ poses[:, :, 3:]], 2)
+    return K_new, poses_new, Hs
+
+
 def normalize_reference_views(database, ids, size, margin, align_pose=None, align_K=None, warp=True):
     """database_utils.py:54-110 (rectify_rot=True, no extra rotations): every reference view is
     re-rendered as a look-at crop of the object at a common apparent size, with the in-plane
@@ -293,16 +322,7 @@ def normalize_reference_views(database, ids, size, margin, align_pose=None, alig
         small = np.linalg.norm(v, axis=1) < 1e-5
         v[small] += 1e-5 * np.sign(v[small])
         angle = -np.arctan2(v[:, 1], v[:, 0]) - np.pi / 2
-    ca, sa = np.cos(angle), np.sin(angle)
-    z, o = np.zeros(n), np.ones(n)
-    Rz = np.stack([np.stack([ca, -sa, z], -1), np.stack([sa, ca, z], -1), np.stack([z, z, o], -1)], 1).astype(np.float32)
-    R = Rz @ R_look                                            # reference builds R_z in float32
-    K_new = np.zeros((n, 3, 3), np.float32)
-    K_new[:, 0, 0] = K_new[:, 1, 1] = tab['f']
-    K_new[:, 0, 2], K_new[:, 1, 2], K_new[:, 2, 2] = size / 2, size / 2, 1
-    Hs = K_new @ R @ tab['Kinv']
-    rect = R.astype(np.float32)
-    poses_new = np.concatenate([rect @ poses[:, :, :3], rect @ poses[:, :, 3:]], 2)
+    K_new, poses_new, Hs = _views_at_angle(tab, angle, size)
     imgs = np.stack([cv2.warpPerspective(database.get_image(i), Hs[k], (size, size), flags=cv2.INTER_LINEAR)
                      for k, i in enumerate(ids)], 0) if warp else None   # warp=False: the caller warps on the device
     return imgs, K_new, poses_new, Hs
@@ -353,6 +373,15 @@ class NormalizedView:
     def denormalize_pose(self, pose):
         R, t = pose[:3, :3], pose[:3, 3]
         return np.concatenate([R, (R @ self.offset / self.scale + t / self.scale)[:, None]], -1).astype(np.float32)
+
+    def normalize_poses(self, poses):
+        """normalize_pose over a stack [n,3,4] (each pose independent of the others)."""
+        R, t = poses[:, :, :3], poses[:, :, 3]
+        return np.concatenate([R, (R @ -self.offset + self.scale * t)[:, :, None]], -1).astype(np.float32)
+
+    def denormalize_poses(self, poses):
+        R, t = poses[:, :, :3], poses[:, :, 3]
+        return np.concatenate([R, (R @ self.offset / self.scale + t / self.scale)[:, :, None]], -1).astype(np.float32)
 
     def get_pose(self, i):
         if i not in self._poses:
@@ -413,47 +442,121 @@ def _normalized_view(database):
     return _VIEW_CACHE[key]
 
 
+def refine_problems(database, ref_ids, que_Ks, in_poses, size=128, ref_num=6, ref_even=False, margin=0.05):
+    """refine_problem(warp=False) for qn independent frames in one pass of stacked numpy operations (the
+    per-frame version costs ~60 small numpy calls; a batch of 10 frames three times per prediction made the
+    host the bottleneck of the batched stages).  Every frame's slice is computed independently of the others,
+    so a frame gets the same numbers alone or inside any batch: refine_problem is the qn = 1 case.
+    Returns stacked arrays: 'que_K' [qn,3,3] f32, 'que_pose' [qn,3,4] f32, 'pose_rect' [qn,3,4] f32, 'que_H'
+    [qn,3,3], 'ref_ids' [qn,ref_num], 'ref_Ks' [qn,ref_num,3,3] f32, 'ref_poses' [qn,ref_num,3,4] f32, 'ref_Hs'
+    [qn,ref_num,3,3], plus 'view' / 'center'."""
+    view = _normalized_view(database)
+    Ks, pose_n = np.asarray(que_Ks), view.normalize_poses(np.asarray(in_poses))
+    qn = len(pose_n)
+    center = view.object_center()
+    c64 = center.astype(np.float64)
+    R, t = pose_n[:, :, :3], pose_n[:, :, 3]
+    # look at the projected object centre (pose_utils.py:52-58), zoom so that the object fills the crop
+    cen_px = _project_center_batch(c64, pose_n, Ks)
+    R_look, f_look = _look_at_batch(cen_px, Ks)
+    # float32 reductions: per frame with the operations the single-frame path has always used (a stacked matmul /
+    # axis-norm may sum in another order: 1 ulp of the crop's focal length)
+    dist = np.asarray([np.linalg.norm(camera_center(p) - center) for p in pose_n])
+    scale = size * (1 - margin) / view.object_diameter() * dist / f_look
+    # look_at_crop with angle 0 (database_utils.py:8-25)
+    K_warp = np.zeros((qn, 3, 3), np.float32)
+    K_warp[:, 0, 0] = K_warp[:, 1, 1] = f_look * scale
+    K_warp[:, 0, 2], K_warp[:, 1, 2], K_warp[:, 2, 2] = size / 2, size / 2, 1
+    que_H = K_warp @ R_look @ np.linalg.inv(Ks)
+    rect = np.concatenate([R_look, np.zeros((qn, 3, 1))], 2).astype(np.float32)
+    pose_warp = np.concatenate([rect[:, :, :3] @ R, rect[:, :, :3] @ pose_n[:, :, 3:] + rect[:, :, 3:]], 2)
+    # the ref_num reference views closest in viewing direction (database_utils.py:125-139)
+    if ref_even and hasattr(view, 'even_subset'):
+        ids_e, _, dirs = view.even_subset(ref_ids, min(128, len(ref_ids)), center)
+        cam_w = -(np.transpose(pose_warp[:, :, :3], (0, 2, 1)) @ pose_warp[:, :, 3:])[:, :, 0] - center[None]
+        qdir = cam_w / np.linalg.norm(cam_w, 2, -1, keepdims=True)
+        order = np.asarray([np.argsort(-(dirs @ qdir[i]))[:ref_num] for i in range(qn)])
+        ids = ids_e[order]
+    else:
+        ids = np.stack([select_views_near_pose(view, center, ref_ids, pose_warp[i], ref_num, ref_even, min(128, len(ref_ids)))
+                        for i in range(qn)], 0)
+    # reference views re-rendered with their in-plane orientation aligned to the query's (database_utils.py:54-110)
+    tab = view.view_table(list(ids.reshape(-1)), size, margin, prefill=ref_ids)
+    ap, aK = pose_warp.astype(np.float64), K_warp.astype(np.float64)
+    Rq = _look_at_batch(_project_center_batch(c64, ap, aK), aK)[0] @ ap[:, :, :3]
+    rel = np.repeat(Rq, ref_num, 0) @ np.transpose(tab['RlookR'], (0, 2, 1))
+    # R = Rx(c) Ry(b) Rz(a)  =>  first row = [cos b cos a, -cos b sin a, sin b]
+    ref_Ks, ref_poses, ref_Hs = _views_at_angle(tab, np.arctan2(-rel[:, 0, 1], rel[:, 0, 0]), size)
+    return {'view': view, 'center': center, 'que_K': K_warp, 'que_pose': pose_warp.astype(np.float32), 'pose_rect': rect,
+            'que_H': que_H, 'ref_ids': ids, 'ref_Ks': ref_Ks.reshape(qn, ref_num, 3, 3).astype(np.float32),
+            'ref_poses': ref_poses.reshape(qn, ref_num, 3, 4).astype(np.float32), 'ref_Hs': ref_Hs.reshape(qn, ref_num, 3, 3)}
+
+
 def refine_problem(database, ref_ids, que_img, que_K, in_pose, size=128, ref_num=6, ref_even=False, margin=0.05,
                    warp=True):
     """Everything refiner.py:285-325 prepares on the host for one refinement step: the query
     look-at crop at the input pose and the `ref_num` nearest reference views re-rendered with
     their in-plane orientation aligned to it.  warp=False skips the OpenCV warps (que_img may be
     None) and only returns their homographies 'que_H' / 'ref_Hs' for g6d_warp_perspective_u8."""
-    view = _normalized_view(database)
-    pose_n = view.normalize_pose(in_pose)
-    center = view.object_center()
-    f_look = look_at_point(pose_n, que_K, center)[1]
-    dist = np.linalg.norm(camera_center(pose_n) - center)
-    scale = size * (1 - margin) / view.object_diameter() * dist / f_look
-    cen_px = project(center[None].astype(np.float64), pose_n, que_K)[0][0]
-    que_crop, K_warp, pose_warp, pose_rect, que_H = look_at_crop(que_img if warp else None, que_K, pose_n, cen_px, 0,
-                                                                 scale, size, size)
-    ids = select_views_near_pose(view, center, ref_ids, pose_warp, ref_num, ref_even, min(128, len(ref_ids)))
-    view.view_table(ids, size, margin, prefill=ref_ids)          # builds the per-object table on first use
-    ref_imgs, ref_Ks, ref_poses, ref_Hs = normalize_reference_views(view, ids, size, margin, pose_warp, K_warp, warp)
-    return {'view': view, 'que_img': que_crop, 'que_K': K_warp.astype(np.float32), 'que_H': que_H, 'ref_Hs': ref_Hs,
-            'que_pose': pose_warp.astype(np.float32), 'pose_rect': pose_rect, 'center': center, 'ref_ids': ids,
-            'ref_imgs': ref_imgs, 'ref_Ks': ref_Ks.astype(np.float32), 'ref_poses': ref_poses.astype(np.float32)}
+    b = refine_problems(database, ref_ids, [que_K], [in_pose], size, ref_num, ref_even, margin)
+    prob = {k: (v if k in ('view', 'center') else v[0]) for k, v in b.items()}
+    prob['que_img'] = prob['ref_imgs'] = None
+    if warp:
+        prob['que_img'] = cv2.warpPerspective(que_img, prob['que_H'], (size, size), flags=cv2.INTER_LINEAR)
+        prob['ref_imgs'] = np.stack([cv2.warpPerspective(prob['view'].get_image(i), H, (size, size), flags=cv2.INTER_LINEAR)
+                                     for i, H in zip(prob['ref_ids'], prob['ref_Hs'])], 0)
+    return prob
+
+
+def _quat_to_matrix_batch(q):
+    """quat_to_matrix over [n,4] (w, x, y, z), float64."""
+    q = np.asarray(q, np.float64)
+    w, x, y, z = q[:, 0], q[:, 1], q[:, 2], q[:, 3]
+    n = w * w + x * x + y * y + z * z
+    ok = n >= np.finfo(np.float64).eps
+    sc = 2.0 / np.where(ok, n, 1.0)
+    m = np.stack([np.stack([1 - sc * (y * y + z * z), sc * (x * y - w * z), sc * (x * z + w * y)], -1),
+                  np.stack([sc * (x * y + w * z), 1 - sc * (x * x + z * z), sc * (y * z - w * x)], -1),
+                  np.stack([sc * (x * z - w * y), sc * (y * z + w * x), 1 - sc * (x * x + y * y)], -1)], 1)
+    m[~ok] = np.eye(3)
+    return m
+
+
+def apply_refinements(probs, quats, offsets, scales):
+    """apply_refinement over the stacked problems of refine_problems: quats [qn,4], offsets [qn,2], scales [qn]
+    -> poses [qn,3,4] float32.  Frame slices are independent; apply_refinement is the qn = 1 case."""
+    pose_in, K = probs['que_pose'].astype(np.float64), probs['que_K'].astype(np.float64)
+    center = probs['center'].astype(np.float64)
+    Rin = pose_in[:, :, :3]
+    cen_in = Rin @ center + pose_in[:, :, 3]
+    A = np.asarray(scales, np.float64)[:, None, None] * _quat_to_matrix_batch(quats)
+    off = np.asarray(offsets, np.float64)
+    cen_que = cen_in + np.concatenate([off, np.zeros((len(off), 1))], 1)
+    A_cen = (A @ cen_in[:, :, None])[:, :, 0]
+    sim_t = cen_que - A_cen
+    # similarity -> rigid: keep the rotation part, move the centre along its new ray to the depth
+    # implied by the scale change
+    U, S, Vt = np.linalg.svd(A)
+    Rdelta = U @ Vt
+    f = (K[:, 0, 0] + K[:, 1, 1]) / 2
+    depth = cen_in[:, 2] / np.mean(np.abs(S), axis=1) * f / f
+    cen_sim = A_cen + sim_t
+    cen_new = cen_sim / cen_sim[:, 2:3] * depth[:, None]
+    Rn = Rdelta @ Rin
+    pose = np.concatenate([Rn, (cen_new - Rn @ center)[:, :, None]], 2)
+    # undo the look-at rectification: then apply the inverse of pose_rect
+    rect = probs['pose_rect']
+    Rt = np.transpose(rect[:, :, :3], (0, 2, 1))
+    inv = np.concatenate([Rt, -Rt @ rect[:, :, 3:]], 2)
+    pose = np.concatenate([inv[:, :, :3] @ pose[:, :, :3], inv[:, :, :3] @ pose[:, :, 3:] + inv[:, :, 3:]], 2)
+    return probs['view'].denormalize_poses(pose)
 
 
 def apply_refinement(prob, quat, offset, scale):
     """refiner.py:333-340: (scale, quaternion, 2-D offset) -> similarity transform about the object
     centre -> rigid pose at the matching depth -> undo the look-at rectification -> undo the
     unit-sphere normalisation (pose_utils.py:217-244)."""
-    pose_in, K, center = prob['que_pose'].astype(np.float64), prob['que_K'].astype(np.float64), prob['center']
-    cen_in = pose_apply(pose_in, center.astype(np.float64))
-    A = float(np.asarray(scale).reshape(-1)[0]) * quat_to_matrix(quat)
-    cen_que = cen_in + np.array([offset[0], offset[1], 0.0])
-    sim_t = cen_que - A @ cen_in
-    # similarity -> rigid: keep the rotation part, move the centre along its new ray to the depth
-    # implied by the scale change
-    U, S, Vt = np.linalg.svd(A)
-    Rdelta = U @ Vt
-    f = np.mean(np.diag(K)[:2])
-    depth = cen_in[2] / np.mean(np.abs(S)) * f / f
-    cen_sim = A @ cen_in + sim_t
-    cen_new = cen_sim / cen_sim[2] * depth
-    R = Rdelta @ pose_in[:3, :3]
-    pose = np.concatenate([R, (cen_new - R @ center)[:, None]], 1)
-    pose = pose_compose(pose, pose_inverse(prob['pose_rect']))
-    return prob['view'].denormalize_pose(pose)
+    probs = {k: (v if k in ('view', 'center') else v[None]) for k, v in prob.items() if k in
+             ('view', 'center', 'que_pose', 'que_K', 'pose_rect')}
+    return apply_refinements(probs, np.asarray(quat, np.float64)[None], np.asarray(offset, np.float64)[None],
+                             [float(np.asarray(scale).reshape(-1)[0])])[0]

@@ -32,6 +32,7 @@ class VolumeRefiner(PackedModule):
         self.ref_database = None
         self.ref_ids = None
         self._ref_dev = {}
+        self._ref_src = {}
 
     # ------------------------------------------------------------------ weights
     def _pack(self):
@@ -185,6 +186,7 @@ class VolumeRefiner(PackedModule):
         self.ref_database = as_object_database(ref_database)
         self.ref_ids = ref_ids
         self._ref_dev = {}          # image id -> device uint8 [rows, cols, 3] (filled on first use)
+        self._ref_src = {}          # image id -> geometry.warp_source() of that tensor
         self.bump_generation()
 
     def _ref_images_dev(self, ids):
@@ -199,6 +201,14 @@ class VolumeRefiner(PackedModule):
                     torch.cuda.current_stream().synchronize()
                     self._ref_dev.update(dev)
         return [self._ref_dev[i] for i in ids]
+
+    def _ref_sources(self, ids):
+        """warp_source() triples of the resident database images `ids` (described once per object)."""
+        if not self._ref_src:
+            from .. import geometry as G
+            dev = self._ref_images_dev(self.ref_ids)
+            self._ref_src.update({i: G.warp_source(t) for i, t in zip(self.ref_ids, dev)})
+        return [self._ref_src[i] for i in ids]
 
     def _refine_warped(self, size):
         """jobs: per pose one query crop followed by its rfn reference crops (qn * (rfn + 1) records)."""
@@ -216,17 +226,16 @@ class VolumeRefiner(PackedModule):
         one D2H of [qn,7].  Returns the refined poses [qn,3,4] (identical to per-frame refine_que_imgs)."""
         from .. import geometry as G
         qn = len(in_poses)
-        probs = [G.refine_problem(self.ref_database, self.ref_ids, None, que_Ks[i], in_poses[i], size, ref_num, ref_even, warp=False)
-                 for i in range(qn)]
+        probs = G.refine_problems(self.ref_database, self.ref_ids, que_Ks, in_poses, size, ref_num, ref_even)
         srcs, mats = [], []
-        for i, prob in enumerate(probs):
-            srcs += [frames_dev[i]] + self._ref_images_dev(list(prob['ref_ids']))
-            mats += [G.perspective_dst_to_src(prob['que_H'])] + [G.perspective_dst_to_src(H) for H in prob['ref_Hs']]
+        for i in range(qn):
+            srcs += [G.warp_source(frames_dev[i])] + self._ref_sources(probs['ref_ids'][i])
+            mats += [G.perspective_dst_to_src(probs['que_H'][i])] + [G.perspective_dst_to_src(H) for H in probs['ref_Hs'][i]]
         cams = ('que_K', 'que_pose', 'ref_Ks', 'ref_poses')
         with torch.no_grad():
-            args = [self._to_dev(G.pack_warp_jobs(srcs, mats))] + [self._to_dev(np.stack([p[k] for p in probs], 0)) for k in cams]
+            args = [self._to_dev(G.pack_warp_jobs(srcs, mats))] + [self._to_dev(probs[k]) for k in cams]
             out = self._to_host(self.stages.run(f'refine_warp{size}', self._refine_warped(size), args))
-        return np.stack([G.apply_refinement(prob, quat=o[:4], offset=o[4:6], scale=2.0 ** o[6]) for prob, o in zip(probs, out)], 0)
+        return G.apply_refinements(probs, out[:, :4], out[:, 4:6], [2.0 ** o[6] for o in out])
 
     def refine_que_imgs(self, que_img, que_K, in_pose, size=128, ref_num=6, ref_even=False, que_dev=None,
                         host_warps=False):

@@ -64,3 +64,38 @@ def test_refine_problem_and_pose_update(db):
     f = E['geo.refine.fixed']
     pose = G.apply_refinement(prob, quat=f[:4], offset=f[4:6], scale=2.0 ** f[6])
     np.testing.assert_allclose(pose, E['geo.refine.pose_out'], rtol=1e-4, atol=1e-4)
+
+
+def test_batched_refinement_geometry_equals_per_frame(db):
+    """refine_problems / apply_refinements (one pass of stacked numpy operations for a batch of frames) give every
+    frame bit for bit what refine_problem / apply_refinement give it alone, for float32 and float64 input poses."""
+    ids = db.get_img_ids()
+    rng = np.random.RandomState(3)
+    poses = []
+    for i in range(12):
+        p = db.get_pose(ids[rng.randint(len(ids))]).astype(np.float64).copy()
+        w = rng.randn(3) * 0.05
+        Wx = np.array([[0, -w[2], w[1]], [w[2], 0, -w[0]], [-w[1], w[0], 0]])
+        p[:, :3] = (np.eye(3) + Wx + Wx @ Wx / 2) @ p[:, :3]        # a small (not exactly orthonormal) rotation is fine here
+        p[:, 3] += rng.randn(3) * 0.02
+        poses.append(p)
+    outs = (rng.randn(12, 7) * 0.05).astype(np.float32)
+    outs[:, 0] += 1
+    keys = ('que_K', 'que_pose', 'pose_rect', 'que_H', 'ref_Ks', 'ref_poses', 'ref_Hs')
+    for dt in (np.float32, np.float64):
+        ps = [p.astype(dt) for p in poses]
+        batch = G.refine_problems(db, ids, [db.K] * len(ps), ps, 128, 6, True)
+        new = G.apply_refinements(batch, outs[:, :4], outs[:, 4:6], [2.0 ** o[6] for o in outs])
+        assert new.dtype == np.float32 and new.shape == (12, 3, 4)
+        for i, p in enumerate(ps):
+            one = G.refine_problem(db, ids, None, db.K, p, 128, 6, True, warp=False)
+            assert [str(v) for v in one['ref_ids']] == [str(v) for v in batch['ref_ids'][i]]
+            for k in keys:
+                assert one[k].dtype == batch[k].dtype and np.array_equal(one[k], batch[k][i]), (k, i)
+            o = outs[i]
+            assert np.array_equal(new[i], G.apply_refinement(one, quat=o[:4], offset=o[4:6], scale=2.0 ** o[6]))
+    # nearest views without the FPS re-spread (ref_even=False) go through the generic per-frame selection
+    b2 = G.refine_problems(db, ids[:40], [db.K] * 3, poses[:3], 128, 6, False)
+    for i in range(3):
+        one = G.refine_problem(db, ids[:40], None, db.K, poses[i], 128, 6, False, warp=False)
+        assert np.array_equal(one['ref_poses'], b2['ref_poses'][i]) and np.array_equal(one['que_H'], b2['que_H'][i])
