@@ -134,7 +134,7 @@ class Gen6DEstimator:
         que_imgs: list / array of uint8 [h,w,3]; que_Ks: [qn,3,3].  Returns (poses [qn,3,4], inter dict of lists)."""
         qn, res = len(que_imgs), self.cfg['ref_resolution']
         que_Ks = [np.asarray(K) for K in que_Ks]
-        frames = self.detector.upload_frame(np.stack(que_imgs, 0))            # [qn,h,w,3] once, for all stages
+        frames = self.detector.upload_frame([np.asarray(f) for f in que_imgs])  # [qn,h,w,3] once, for all stages
         inter = {}
         if pose_inits is None:
             det = self.detector.detect_que_imgs(None, que_dev=frames)
@@ -142,9 +142,9 @@ class Gen6DEstimator:
             sel = self.selector.select_from_frames(frames, Ms, res)
             inter.update(det_position=det['positions'], det_scale_r2q=det['scales'], det_que_img=sel['que_imgs'],
                          sel_angle_r2q=sel['angles'], sel_scores=sel['scores'], sel_ref_idx=sel['ref_idx'])
-            poses = np.stack([G.pose_from_similarity(det['positions'][i], det['scales'][i], sel['angles'][i],
-                                                     self.ref_info['poses'][sel['ref_idx'][i]], self.ref_info['Ks'][sel['ref_idx'][i]],
-                                                     que_Ks[i], self.ref_info['center']) for i in range(qn)], 0)
+            ridx = np.asarray(sel['ref_idx'])
+            poses = G.poses_from_similarity(det['positions'], det['scales'], sel['angles'], self.ref_info['poses'][ridx],
+                                            self.ref_info['Ks'][ridx], np.stack(que_Ks, 0), self.ref_info['center'])
         else:
             poses = np.stack(pose_inits, 0)
         if self.refiner is not None:

@@ -329,28 +329,47 @@ def normalize_reference_views(database, ids, size, margin, align_pose=None, alig
 
 
 # ------------------------------------------------------------------------------------------ pose from detection + selection
+def poses_from_similarity(positions, scales_r2q, angles_r2q, ref_poses, ref_Ks, que_Ks, center):
+    """pose_from_similarity for n independent detections in one pass of stacked operations: positions [n,2],
+    scales / angles [n], ref_poses [n,3,4], ref_Ks / que_Ks [n,3,3] -> poses [n,3,4] float64.  Slices are
+    independent: a detection gets the same pose alone or inside a batch."""
+    center = np.asarray(center, np.float64)
+    ref_poses, ref_Ks, que_Ks = np.asarray(ref_poses), np.asarray(ref_Ks), np.asarray(que_Ks)
+    n = len(ref_poses)
+    ref_cen = _project_center_batch(center, ref_poses, ref_Ks)
+    # query -> reference similarity (similarity_2d), then inverted (reference -> query)
+    sc, ang = 1.0 / np.asarray(scales_r2q), -np.asarray(angles_r2q)
+    c, s_ = np.cos(ang), np.sin(ang)
+    M = np.zeros((n, 3, 3))
+    M[:, 0, 0], M[:, 0, 1], M[:, 1, 0], M[:, 1, 1], M[:, 2, 2] = sc * c, sc * -s_, sc * s_, sc * c, 1
+    M[:, :2, 2] = ref_cen - (M[:, :2, :2] @ np.asarray(positions, np.float64)[:, :, None])[:, :, 0]
+    M_r2q = np.linalg.inv(M)
+    que_cen = (M_r2q[:, :2, :2] @ ref_cen[:, :, None])[:, :, 0] + M_r2q[:, :2, 2]
+    bearing = (np.linalg.inv(que_Ks) @ np.concatenate([que_cen, np.ones((n, 1))], 1)[:, :, None])[:, :, 0]
+    bearing_xy = bearing[:, :2] / bearing[:, 2:3]
+    scale = np.sqrt(np.linalg.det(M_r2q[:, :2, :2]))
+    rotation = np.arctan2(M_r2q[:, 1, 0], M_r2q[:, 0, 0])
+    que_f, ref_f = (que_Ks[:, 0, 0] + que_Ks[:, 1, 1]) / 2, (ref_Ks[:, 0, 0] + ref_Ks[:, 1, 1]) / 2
+    que_f_ray = np.sqrt(que_f ** 2 + np.linalg.norm(bearing_xy * que_f[:, None], axis=1) ** 2)
+    ref_dist = np.asarray([np.linalg.norm(camera_center(p) - center) for p in ref_poses])
+    que_dist = ref_dist * que_f_ray / ref_f / scale
+    ray = np.concatenate([bearing_xy, np.ones((n, 1))], 1)
+    cen3d = ray / np.linalg.norm(ray, axis=1)[:, None] * que_dist[:, None]
+    # look_at_rotation(bearing_xy).T @ (rot_z(rotation) @ R_ref)
+    R_look = _look_at_batch(bearing_xy, np.broadcast_to(np.eye(3), (n, 3, 3)))[0]
+    cr, sr = np.cos(rotation), np.sin(rotation)
+    Rz = np.zeros((n, 3, 3))
+    Rz[:, 0, 0], Rz[:, 0, 1], Rz[:, 1, 0], Rz[:, 1, 1], Rz[:, 2, 2] = cr, -sr, sr, cr, 1
+    R = np.transpose(R_look, (0, 2, 1)) @ (Rz @ ref_poses[:, :, :3])
+    return np.concatenate([R, (cen3d - R @ center)[:, :, None]], 2)
+
+
 def pose_from_similarity(position, scale_r2q, angle_r2q, ref_pose, ref_K, que_K, center):
     """estimate_pose_from_similarity_transform_compose (pose_utils.py:104-111 -> :12-46): the 2-D
     similarity (detected position / scale, selected in-plane angle) that maps the reference crop
     into the query image fixes the object's bearing, depth and in-plane rotation."""
-    center = np.asarray(center, np.float64)
-    ref_cen = project(center[None], ref_pose, ref_K)[0][0]
-    # query -> reference similarity, then inverted (reference -> query)
-    M_q2r = similarity_2d(position, 1.0 / scale_r2q, -angle_r2q, ref_cen)
-    M_r2q = np.linalg.inv(M_q2r)
-    que_cen = M_r2q[:2, :2] @ ref_cen + M_r2q[:2, 2]
-    bearing = np.linalg.inv(que_K) @ np.array([que_cen[0], que_cen[1], 1.0])
-    bearing_xy = bearing[:2] / bearing[2]
-    scale = np.sqrt(np.linalg.det(M_r2q[:2, :2]))
-    rotation = np.arctan2(M_r2q[1, 0], M_r2q[0, 0])
-    que_f, ref_f = (que_K[0, 0] + que_K[1, 1]) / 2, (ref_K[0, 0] + ref_K[1, 1]) / 2
-    que_f_ray = np.sqrt(que_f ** 2 + np.linalg.norm(bearing_xy * que_f) ** 2)
-    ref_dist = np.linalg.norm(camera_center(ref_pose) - center)
-    que_dist = ref_dist * que_f_ray / ref_f / scale
-    ray = np.array([bearing_xy[0], bearing_xy[1], 1.0])
-    cen3d = ray / np.linalg.norm(ray) * que_dist
-    R = look_at_rotation(bearing_xy).T @ (rot_z(rotation) @ ref_pose[:, :3])
-    return np.concatenate([R, (cen3d - R @ center)[:, None]], 1)
+    return poses_from_similarity(np.asarray(position)[None], np.asarray(scale_r2q)[None], np.asarray(angle_r2q)[None],
+                                 np.asarray(ref_pose)[None], np.asarray(ref_K)[None], np.asarray(que_K)[None], center)[0]
 
 
 # ------------------------------------------------------------------------------------------ refinement bookkeeping
