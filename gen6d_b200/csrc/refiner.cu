@@ -299,172 +299,6 @@ __global__ void __launch_bounds__(256, 2) ref_volume_fill_c128_kernel(const VolP
     }
 }
 
-// ---- volume fill, v4: tap footprints reused along the k-runs ---------------------------------------
-// v3 is bound by the L1 data pipe (28 taps x 512 B per voxel).  Consecutive voxels of a k-run project less than
-// one feature pixel apart in every view, so the 2x2 bilinear footprint of voxel k+1 is that of voxel k, or that
-// footprint moved by one pixel along one axis (two of its four pixels are already in registers), far more often
-// than it is a new one.  Phase A additionally stores a footprint key (y0 * 1024 + x0, biased positive); phase B walks
-// four voxels of the run per view, compares keys (warp-uniform: all lanes of a warp work on the same voxel) and
-// loads only the pixels it does not hold.  Views are the OUTER loop now, so the per-view samples cannot all be
-// kept for the two-pass deviation: the unbiased std uses deviations from the first view's sample,
-//   var = (sum d^2 - (sum d)^2 / R) / (R - 1),  d_v = s_v - s_0,
-// which has no cancellation beyond that of the data itself (d are differences of like quantities) and differs
-// from the two-pass value by a few ulp.
-template <int RT, bool BRANCHY>
-__global__ void __launch_bounds__(256, 2) ref_volume_fill_c128_v4_kernel(const VolParams p) {
-    constexpr int C = 128;
-    constexpr int NV = RT + 1;                    // views: RT references + the query
-    __shared__ float sP[NV][12];
-    __shared__ int4 s_idx[kBrickVox][NV];
-    __shared__ float4 s_w[kBrickVox][NV];
-    __shared__ int s_key[kBrickVox][NV];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int sn = p.sn;
-    const int nbk = (sn + 7) / 8, nbj = (sn + 3) / 4, nbi = (sn + 1) / 2;
-    const int bricks = nbi * nbj * nbk;
-    const int qi = blockIdx.x / bricks;
-    int b = blockIdx.x % bricks;
-    const int bk = b % nbk; b /= nbk;
-    const int bj = b % nbj;
-    const int bi = b / nbj;
-
-    if (threadIdx.x < NV * 12) {                  // P_v = K_v @ [R|t]_v (refiner.py:227,243)
-        const int v = threadIdx.x / 12, e = threadIdx.x % 12, r = e / 4, c = e % 4;
-        const float* K = v < RT ? p.ref_Ks + ((long long)qi * RT + v) * 9 : p.que_Ks + (long long)qi * 9;
-        const float* T = v < RT ? p.ref_poses + ((long long)qi * RT + v) * 12 : p.que_poses + (long long)qi * 12;
-        sP[v][e] = fmaf(K[r * 3 + 0], T[c], fmaf(K[r * 3 + 1], T[4 + c], K[r * 3 + 2] * T[8 + c]));
-    }
-    __syncthreads();
-
-    // ---- phase A (as v3, plus the footprint key)
-    {
-        const float* qp = p.que_poses + (long long)qi * 12;
-        const float r00 = qp[0], r01 = qp[1], r02 = qp[2], r10 = qp[4], r11 = qp[5], r12 = qp[6], r20 = qp[8], r21 = qp[9],
-                    r22 = qp[10];
-        const float step = 2.f / (float)(sn - 1);
-        auto lin = [&](int a) { return a < sn / 2 ? -1.f + step * (float)a : 1.f - step * (float)(sn - 1 - a); };   // torch.linspace
-        for (int e = threadIdx.x; e < kBrickVox * NV; e += 256) {
-            const int n = e / NV, v = e - n * NV;
-            const int i = min(bi * 2 + (n >> 5), sn - 1), j = min(bj * 4 + ((n >> 3) & 3), sn - 1), k = min(bk * 8 + (n & 7), sn - 1);
-            const float* P = sP[v];
-            const float ci = lin(i), cj = lin(j), ck = lin(k);
-            const float vx = fmaf(ci, r00, fmaf(cj, r10, ck * r20));          // row vector @ R_in (refiner.py:216-220)
-            const float vy = fmaf(ci, r01, fmaf(cj, r11, ck * r21));
-            const float vz = fmaf(ci, r02, fmaf(cj, r12, ck * r22));
-            const float px = fmaf(vx, P[0], fmaf(vy, P[1], fmaf(vz, P[2], P[3])));
-            const float py = fmaf(vx, P[4], fmaf(vy, P[5], fmaf(vz, P[6], P[7])));
-            float pz = fmaf(vx, P[8], fmaf(vy, P[9], fmaf(vz, P[10], P[11])));
-            if (pz < 1e-4f) pz = 1e-4f;                                       // refiner.py:199-200
-            const float u = px / pz, vv = py / pz;
-            const float gx = ((u + 0.5f) / (float)p.img_w - 0.5f) * 2.f;      // operator.py:4-17
-            const float gy = ((vv + 0.5f) / (float)p.img_h - 0.5f) * 2.f;
-            const float ix = ((gx + 1.f) * (float)p.fw - 1.f) * 0.5f;         // grid_sample, align_corners=False
-            const float iy = ((gy + 1.f) * (float)p.fh - 1.f) * 0.5f;
-            const float fx0 = floorf(ix), fy0 = floorf(iy);
-            const float lx = ix - fx0, ly = iy - fy0;
-            const bool close_by = (fx0 > -2.f) && (fx0 < (float)p.fw + 1.f) && (fy0 > -2.f) && (fy0 < (float)p.fh + 1.f);
-            const int x0 = close_by ? (int)fx0 : -10, y0 = close_by ? (int)fy0 : -10;
-            int ti[4]; float tw[4];
-#pragma unroll
-            for (int t = 0; t < 4; ++t) {
-                const int xx = x0 + (t & 1), yy = y0 + (t >> 1);
-                const bool inb = (unsigned)xx < (unsigned)p.fw && (unsigned)yy < (unsigned)p.fh;
-                // out-of-bounds taps (zeros padding) keep a valid address and get weight 0: branch-free gather
-                ti[t] = inb ? (yy * p.fw + xx) * C : 0;
-                tw[t] = inb ? ((t & 1) ? lx : 1.f - lx) * ((t >> 1) ? ly : 1.f - ly) : 0.f;
-            }
-            s_idx[n][v] = make_int4(ti[0], ti[1], ti[2], ti[3]);
-            s_w[n][v] = make_float4(tw[0], tw[1], tw[2], tw[3]);
-            // a reused register of an out-of-bounds position holds pixel 0 in both footprints, and weight 0 in both
-            s_key[n][v] = (y0 + 16) * 1024 + (x0 + 16);
-        }
-    }
-    __syncthreads();
-
-    // ---- phase B: warp = one k-run of 8 voxels in two halves of 4, lane = channels [4 lane, 4 lane + 4)
-    const long long fsz = (long long)p.fh * p.fw * C;
-    const long long nvox = (long long)sn * sn * sn;
-    const int i = bi * 2 + (warp >> 2), j = bj * 4 + (warp & 3);
-    if (i >= sn || j >= sn) return;                                           // warp-uniform
-    constexpr float inv_r = 1.f / (float)RT;
-    constexpr float inv_u = 1.f / (float)(RT - 1);                            // unbiased (torch.std default, refiner.py:237)
-    auto axpy = [](float4& a, const float4 f, float w) {
-        a.x = fmaf(f.x, w, a.x); a.y = fmaf(f.y, w, a.y); a.z = fmaf(f.z, w, a.z); a.w = fmaf(f.w, w, a.w);
-    };
-#pragma unroll 1
-    for (int half = 0; half < 2; ++half) {
-        const int k0 = bk * 8 + half * 4;
-        if (k0 >= sn) break;                                                  // warp-uniform
-        const int n0 = warp * 8 + half * 4;
-        const long long orow0 = (long long)qi * nvox + ((long long)i * sn + j) * sn + k0;
-        float4 s0[4], sd[4], sq[4];
-#pragma unroll 1                                                               // (unrolled: 20 registers spilled at the 128 cap)
-        for (int v = 0; v < NV; ++v) {
-            const float* base = (v < RT ? p.ref_feats + ((long long)qi * RT + v) * fsz : p.que_feats + (long long)qi * fsz) + lane * 4;
-            float4 c0, c1, c2, c3;
-            c0 = c1 = c2 = c3 = make_float4(0.f, 0.f, 0.f, 0.f);
-            int ckey = -(1 << 24);
-#pragma unroll
-            for (int t4 = 0; t4 < 4; ++t4) {
-                const int4 ti = s_idx[n0 + t4][v];
-                const float4 tw = s_w[n0 + t4][v];
-                const int key = s_key[n0 + t4][v];
-                const int delta = key - ckey;                                 // warp-uniform
-                ckey = key;
-                float4 f0, f1, f2, f3;
-                if constexpr (BRANCHY) {
-                    if (delta == 0) { f0 = c0; f1 = c1; f2 = c2; f3 = c3; }
-                    else if (delta == 1) { f0 = c1; f2 = c3; f1 = ldg_at(base, ti.y); f3 = ldg_at(base, ti.w); }
-                    else if (delta == -1) { f1 = c0; f3 = c2; f0 = ldg_at(base, ti.x); f2 = ldg_at(base, ti.z); }
-                    else if (delta == 1024) { f0 = c2; f1 = c3; f2 = ldg_at(base, ti.z); f3 = ldg_at(base, ti.w); }
-                    else if (delta == -1024) { f2 = c0; f3 = c1; f0 = ldg_at(base, ti.x); f1 = ldg_at(base, ti.y); }
-                    else { f0 = ldg_at(base, ti.x); f1 = ldg_at(base, ti.y); f2 = ldg_at(base, ti.z); f3 = ldg_at(base, ti.w); }
-                } else {
-                    // predicated loads (issued without waiting for the selects of the previous voxel) + selects
-                    const bool same = delta == 0, xp = delta == 1, xm = delta == -1, yp = delta == 1024, ym = delta == -1024;
-                    const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-                    const float4 l0 = (same | xp | yp) ? z : ldg_at(base, ti.x);
-                    const float4 l1 = (same | xm | yp) ? z : ldg_at(base, ti.y);
-                    const float4 l2 = (same | xp | ym) ? z : ldg_at(base, ti.z);
-                    const float4 l3 = (same | xm | ym) ? z : ldg_at(base, ti.w);
-                    f0 = same ? c0 : (xp ? c1 : (yp ? c2 : l0));
-                    f1 = same ? c1 : (xm ? c0 : (yp ? c3 : l1));
-                    f2 = same ? c2 : (xp ? c3 : (ym ? c0 : l2));
-                    f3 = same ? c3 : (xm ? c2 : (ym ? c1 : l3));
-                }
-                c0 = f0; c1 = f1; c2 = f2; c3 = f3;
-                float4 a;
-                a.x = f0.x * tw.x; a.y = f0.y * tw.x; a.z = f0.z * tw.x; a.w = f0.w * tw.x;
-                axpy(a, f1, tw.y); axpy(a, f2, tw.z); axpy(a, f3, tw.w);
-                if (v == 0) {
-                    s0[t4] = a;
-                    sd[t4] = sq[t4] = make_float4(0.f, 0.f, 0.f, 0.f);
-                } else if (v < RT) {
-                    float d;
-                    d = a.x - s0[t4].x; sd[t4].x += d; sq[t4].x = fmaf(d, d, sq[t4].x);
-                    d = a.y - s0[t4].y; sd[t4].y += d; sq[t4].y = fmaf(d, d, sq[t4].y);
-                    d = a.z - s0[t4].z; sd[t4].z += d; sq[t4].z = fmaf(d, d, sq[t4].z);
-                    d = a.w - s0[t4].w; sd[t4].w += d; sq[t4].w = fmaf(d, d, sq[t4].w);
-                } else if (k0 + t4 < sn) {
-                    __stcs(reinterpret_cast<float4*>(p.mean_in + (orow0 + t4) * (2 * C) + C + lane * 4), a);    // query sample
-                }
-            }
-        }
-#pragma unroll
-        for (int t4 = 0; t4 < 4; ++t4) {
-            if (k0 + t4 >= sn) break;                                         // warp-uniform
-            float4 mean, var, sdv;
-            mean.x = fmaf(sd[t4].x, inv_r, s0[t4].x); mean.y = fmaf(sd[t4].y, inv_r, s0[t4].y);
-            mean.z = fmaf(sd[t4].z, inv_r, s0[t4].z); mean.w = fmaf(sd[t4].w, inv_r, s0[t4].w);
-            var.x = fmaxf(fmaf(-sd[t4].x * inv_r, sd[t4].x, sq[t4].x), 0.f); var.y = fmaxf(fmaf(-sd[t4].y * inv_r, sd[t4].y, sq[t4].y), 0.f);
-            var.z = fmaxf(fmaf(-sd[t4].z * inv_r, sd[t4].z, sq[t4].z), 0.f); var.w = fmaxf(fmaf(-sd[t4].w * inv_r, sd[t4].w, sq[t4].w), 0.f);
-            sdv.x = sqrtf(var.x * inv_u); sdv.y = sqrtf(var.y * inv_u); sdv.z = sqrtf(var.z * inv_u); sdv.w = sqrtf(var.w * inv_u);
-            __stcs(reinterpret_cast<float4*>(p.mean_in + (orow0 + t4) * (2 * C) + lane * 4), mean);
-            __stcs(reinterpret_cast<float4*>(p.stdv + (orow0 + t4) * C + lane * 4), sdv);
-        }
-    }
-}
-
 // x [M,K] -> out [M,7]: quaternion (normalised, F.normalize eps 1e-12), 2-D offset, log2 scale
 __global__ void ref_pose_heads_kernel(const float* __restrict__ x, const float* __restrict__ w,
                                       const float* __restrict__ b, float* __restrict__ out, int K) {
@@ -502,12 +336,9 @@ extern "C" int g6d_ref_volume_fill(const float* ref_feats, const float* que_feat
                 Q, R, fh, fw, C, sn, img_h, img_w};
     G6D_REQUIRE(R <= 7, "g6d_ref_volume_fill: at most 7 reference views (7 + query fill the 8 projection lanes x 4 voxels)");
     const long long bricks = (long long)((sn + 1) / 2) * ((sn + 3) / 4) * ((sn + 7) / 8);
-    const char* e = getenv("G6D_R2_V");                 // 2 / 3 / 4 (branchy reuse) / 5 (predicated reuse); default 3
-    const int ver = (e && e[0] >= '2' && e[0] <= '5') ? e[0] - '0' : 3;
-    const bool fits = R == 6 && C == 128 && fh + 17 < 1000 && fw + 17 < 1000;
-    if (fits && ver == 4) ref_volume_fill_c128_v4_kernel<6, true><<<(unsigned)(Q * bricks), 256, 0, as_stream(stream)>>>(p);
-    else if (fits && ver == 5) ref_volume_fill_c128_v4_kernel<6, false><<<(unsigned)(Q * bricks), 256, 0, as_stream(stream)>>>(p);
-    else if (fits && ver == 3) ref_volume_fill_c128_kernel<6><<<(unsigned)(Q * bricks), 256, 0, as_stream(stream)>>>(p);
+    static int v3 = -1;
+    if (v3 < 0) { const char* e = getenv("G6D_R2_V"); v3 = (e && e[0] == '2') ? 0 : 1; }
+    if (R == 6 && C == 128 && v3) ref_volume_fill_c128_kernel<6><<<(unsigned)(Q * bricks), 256, 0, as_stream(stream)>>>(p);
     else if (R == 6) ref_volume_fill_kernel<6><<<(unsigned)(Q * bricks), 256, 0, as_stream(stream)>>>(p);
     else ref_volume_fill_kernel<0><<<(unsigned)(Q * bricks), 256, 0, as_stream(stream)>>>(p);
     G6D_CHECK_LAUNCH("g6d_ref_volume_fill");
