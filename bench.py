@@ -47,10 +47,10 @@ def pick_batch(steps, workers):
         return E2E_BATCH
     if steps % workers == 0:
         per_lane = steps // workers
-        for b in range(min(E2E_MAX_BATCH, per_lane), 3, -1):
-            if per_lane % b == 0:
+        for b in range(min(E2E_MAX_BATCH, per_lane), 0, -1):
+            if per_lane % b == 0 and (b >= 4 or b == per_lane):
                 return b
-    return 4
+    return 4 if steps >= 4 * workers else 1      # very short runs: frame by frame (no batch larger than the run)
 METRIC = 'poses/sec end-to-end (128^2 crop, 64 refs, 3 refine iters)'
 WORKLOAD = ('full estimator detect->select->3x refine: synthetic 480x640 frame, detector 32 refs x 4 scales, '
             'selector 64 refs x 5 angles, refiner 6 views 32^3 volume, seeded random weights')

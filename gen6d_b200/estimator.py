@@ -181,6 +181,8 @@ class Gen6DEstimator:
         another batch's kernels.  Same results as predict(); returns [(pose, inter)] (inter of a batched
         frame holds that frame's slices)."""
         from concurrent.futures import ThreadPoolExecutor
+        if len(que_imgs) == 0:
+            return []
         # The clones share weights / reference features by reference and own captured graphs over them:
         # rebuild them whenever any module's state changed (build() on another object, load_state_dict).
         if getattr(self, '_workers', None) is None or len(self._workers) != workers or self._workers_gen != self._generation():

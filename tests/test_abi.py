@@ -44,3 +44,21 @@ def test_compute_fails_loudly_without_cuda():
     det = name2network['detector']({})
     with pytest.raises(Exception):
         det.load_ref_imgs(np.zeros((2, 128, 128, 3), np.uint8))
+
+
+def test_bench_batch_choice_deals_lanes_evenly():
+    """bench.py's pick_batch: the timed region of `steps` poses is dealt to the lanes as equal numbers of full batches
+    whenever the step count allows it (the driver's 20 steps on 2 lanes -> 2 x 10)."""
+    import importlib.util
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location('g6d_bench', os.path.join(root, 'bench.py'))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    if bench.E2E_BATCH > 0:
+        pytest.skip('G6D_E2E_BATCH overrides the choice')
+    want = {(20, 2): 10, (16, 2): 8, (24, 2): 6, (14, 2): 7, (20, 1): 10, (4, 2): 2, (2, 2): 1, (22, 2): 4, (5, 2): 1,
+            (9, 2): 4, (40, 2): 10, (30, 3): 10}
+    for (steps, lanes), b in want.items():
+        assert bench.pick_batch(steps, lanes) == b, (steps, lanes)
+        if steps % lanes == 0 and (steps // lanes) % b == 0:
+            assert (steps // b) % lanes == 0          # every lane runs the same number of batches

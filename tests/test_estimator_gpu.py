@@ -83,6 +83,10 @@ def test_predict_many_equals_predict(est):
     par = e.predict_many(imgs, Ks, workers=2)
     for a, (b, _) in zip(seq, par):
         np.testing.assert_allclose(a, b, atol=1e-5)
+    assert e.predict_many([], [], workers=2, batch=4) == []          # nothing to do: no worker is woken
+    one = e.predict_many(imgs[:1], Ks[:1], workers=2, batch=4)       # fewer frames than a batch, fewer batches than workers
+    assert len(one) == 1
+    np.testing.assert_allclose(one[0][0], seq[0], atol=1e-5)
 
 
 def test_predict_batch_equals_predict(est):
