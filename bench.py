@@ -35,6 +35,7 @@ sys.path.insert(0, ROOT)
 E2E_WORKERS = int(os.environ.get('G6D_E2E_WORKERS', '2'))      # host threads / CUDA streams per GPU (predict_many / device lanes)
 E2E_BATCH = int(os.environ.get('G6D_E2E_BATCH', '0'))          # frames per batched stage (predict_batch); 0 = pick_batch(steps)
 E2E_MAX_BATCH = 10
+DEVICE_GLUE = os.environ.get('G6D_DEVICE_GLUE', '0') != '0'     # camera algebra between the stages on the device: one graph per batch
 
 
 def pick_batch(steps, workers):
@@ -351,7 +352,7 @@ def run_ours(args, rank, world, local_rank):
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
-    est, db = syn.build_estimator()
+    est, db = syn.build_estimator(device_glue=DEVICE_GLUE)
     note('estimator built')
     ids = db.get_img_ids()
     frames = [ids[(7 + rank * 13 + i * 3) % len(ids)] for i in range(8)]   # different frames per rank
@@ -366,7 +367,7 @@ def run_ours(args, rank, world, local_rank):
     batch_imgs = [db.get_image(frames[i % len(frames)]) for i in range(Bt)]
 
     def record(e):
-        rec, mods = [], [m for m in (e.detector, e.selector, e.refiner) if m is not None]
+        rec, mods = [], [m for m in (e, e.detector, e.selector, e.refiner) if m is not None]     # e: the whole-prediction graph (device_glue)
         for m in mods:
             def wrapped(name, fn, inputs, _m=m, _o=m.stages.run):
                 rec.append((_m, name, fn, list(inputs)))

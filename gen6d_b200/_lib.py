@@ -31,12 +31,35 @@ class DetMaps(C.Structure):
                 ('mu', C.c_float * 3), ('inv_sigma', C.c_float * 3), ('clip', C.c_float)]
 
 
+class GlueCamera(C.Structure):        # g6d_glue_camera (20 doubles: a float64 [qn, 20] numpy array has this layout)
+    _fields_ = [('K', C.c_double * 9), ('Kinv', C.c_double * 9), ('f', C.c_double), ('f_sq', C.c_double)]
+
+
+class GlueRefs(C.Structure):          # g6d_glue_refs
+    _fields_ = [('poses', C.c_void_p), ('cen', C.c_void_p), ('f', C.c_void_p), ('dist', C.c_void_p), ('center', C.c_double * 3)]
+
+
+class GlueViews(C.Structure):         # g6d_glue_views
+    _fields_ = [('poses', C.c_void_p), ('R_look', C.c_void_p), ('RlookR', C.c_void_p), ('f', C.c_void_p), ('Kinv', C.c_void_p),
+                ('src', C.c_void_p), ('rows', C.c_void_p), ('cols', C.c_void_p), ('even_idx', C.c_void_p), ('even_dirs', C.c_void_p),
+                ('n_views', C.c_int), ('n_even', C.c_int), ('ref_num', C.c_int), ('size', C.c_int),
+                ('norm_scale', C.c_double), ('norm_offset', C.c_float * 3), ('size_scale', C.c_float)]
+
+
 P, I, L, F = C.c_void_p, C.c_int, C.c_longlong, C.c_float
 _SIGNATURES = {
     'g6d_preprocess_u8': [P, P, L, I, I, P],
     'g6d_imagenet_norm': [P, P, L, I, I, P],
     'g6d_warp_perspective_u8': [P, I, P, I, I, P],
     'g6d_warp_affine_u8': [P, I, P, I, I, P],
+    'g6d_glue_detection_jobs': [P, P, I, I, I, I, P, P],
+    'g6d_glue_detection_jobs_host': [P, P, I, I, I, I, P],
+    'g6d_glue_initial_poses': [P, P, P, C.POINTER(GlueRefs), P, I, P, P],
+    'g6d_glue_initial_poses_host': [P, P, P, C.POINTER(GlueRefs), P, I, P],
+    'g6d_glue_refine_problems': [C.POINTER(GlueViews), P, P, I, I, P, I, I, P, P, P, P, P, P, P, P],
+    'g6d_glue_refine_problems_host': [C.POINTER(GlueViews), P, P, I, I, P, I, I, P, P, P, P, P, P, P],
+    'g6d_glue_apply_refinements': [C.POINTER(GlueViews), P, P, P, P, I, P, P],
+    'g6d_glue_apply_refinements_host': [C.POINTER(GlueViews), P, P, P, P, I, P],
     'g6d_nchw_to_nhwc': [P, P, I, I, I, I, I, P],
     'g6d_nhwc_to_nchw': [P, P, I, I, I, I, I, P],
     'g6d_resize_bilinear': [P, P, I, I, I, I, I, I, I, I, P],

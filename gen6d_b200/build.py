@@ -11,6 +11,7 @@ LIB = os.path.join(HERE, 'libgen6d_b200.so')
 STAMP = os.path.join(HERE, '.libgen6d_b200.hash')
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', '-std=c++17',
               '-Xcompiler', '-fPIC']
+NO_FMA = ('glue.cu',)
 
 
 def sources():
@@ -24,7 +25,7 @@ def _digest():
     for f in files:
         h.update(f.encode())
         h.update(open(f, 'rb').read())
-    h.update(' '.join(NVCC_FLAGS).encode())
+    h.update(' '.join(NVCC_FLAGS + list(NO_FMA)).encode())
     return h.hexdigest()
 
 
@@ -41,7 +42,8 @@ def build(force=False, verbose=False):
     for src in sources():
         obj = os.path.join(objdir, os.path.basename(src)[:-3] + '.o')
         objs.append(obj)
-        cmd = [nvcc] + NVCC_FLAGS + (['-Xptxas', '-v'] if verbose else []) + ['-c', src, '-o', obj]
+        extra = ['-fmad=false'] if os.path.basename(src) in NO_FMA else []      # numpy-like rounding (glue_math.cuh)
+        cmd = [nvcc] + NVCC_FLAGS + extra + (['-Xptxas', '-v'] if verbose else []) + ['-c', src, '-o', obj]
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
     failed = False
     for src, p in procs:

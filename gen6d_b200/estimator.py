@@ -11,7 +11,9 @@ import torch
 import yaml
 
 from . import geometry as G
+from . import glue
 from . import ops
+from .graphs import StageCache
 from .network import name2network
 
 
@@ -27,6 +29,8 @@ class Gen6DEstimator:
         'device_build': False,    # True: cut the 64 + 5x64 reference crops of build() with the device warp kernel (row f2)
         'host_warps': False,      # True: keep the between-stage crops on the host in OpenCV, as the reference does
         'host_threads': None,     # OpenCV / torch-CPU threads for the host geometry (None: min(8, usable CPUs))
+        'device_glue': False,     # True: predict_batch keeps the camera algebra between the stages on the device -- the
+                                  # whole batch prediction is ONE captured graph (csrc/glue.cu), no host round trips
     }
 
     def __init__(self, cfg, modules=None):
@@ -35,6 +39,8 @@ class Gen6DEstimator:
         synthetic checkpoints); otherwise they are loaded like estimator.py:117-125 does."""
         self.cfg = {**self.default_cfg, **cfg}
         self.ref_info = {}
+        self.stages = StageCache()        # whole-prediction graphs of the device-glue path
+        self._glue = None
         G.configure_host_threads(self.cfg['host_threads'])
         if modules is not None:
             self.detector, self.selector = modules['detector'], modules['selector']
@@ -135,6 +141,8 @@ class Gen6DEstimator:
         qn, res = len(que_imgs), self.cfg['ref_resolution']
         que_Ks = [np.asarray(K) for K in que_Ks]
         frames = self.detector.upload_frame([np.asarray(f) for f in que_imgs])  # [qn,h,w,3] once, for all stages
+        if self.cfg['device_glue'] and pose_inits is None and self._glue_possible():
+            return self._predict_batch_device(frames, que_Ks)
         inter = {}
         if pose_inits is None:
             det = self.detector.detect_que_imgs(None, que_dev=frames)
@@ -155,11 +163,71 @@ class Gen6DEstimator:
             inter['refine_poses'] = chain
         return poses, inter
 
+    # ------------------------------------------------------------------ device-resident prediction
+    def _glue_possible(self):
+        return self.refiner is not None and getattr(self.selector.comm, 'capturable', False) and not self.cfg['host_warps']
+
+    def _glue_state(self):
+        """Device tables of the camera algebra (glue.py), rebuilt when any module's state changed."""
+        gen = self._generation()
+        if self._glue is None or self._glue['gen'] != gen:
+            dev = self.detector.device
+            up = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+            refs = glue.selector_refs(self.ref_info)
+            refs_dev = {k: up(refs[k]) for k in ('poses', 'cen', 'f', 'dist')}
+            tables = glue.refiner_views(self.refiner.ref_database, self.refiner.ref_ids, 128, 6)
+            src = self.refiner._ref_sources(self.refiner.ref_ids)
+            views_dev = {k: up(tables[k]) for k in ('poses', 'R_look', 'RlookR', 'f', 'Kinv', 'even_idx', 'even_dirs')}
+            views_dev['src'] = up(np.asarray([s[0] for s in src], np.uint64).view(np.int64))
+            views_dev['rows'], views_dev['cols'] = up(np.asarray([s[1] for s in src], np.int32)), up(np.asarray([s[2] for s in src], np.int32))
+            torch.cuda.current_stream().synchronize()
+            ptr = lambda d: {k: t.data_ptr() for k, t in d.items()}
+            self._glue = {'gen': gen, 'keep': (refs_dev, views_dev), 'tables': tables,
+                          'refs': glue.refs_struct({**ptr(refs_dev), 'center': refs['center']}),
+                          'views': glue.views_struct(ptr(views_dev), tables, views_dev['src'].data_ptr(), views_dev['rows'].data_ptr(),
+                                                     views_dev['cols'].data_ptr())}
+            self.stages.clear()
+        return self._glue
+
+    def _predict_device_fn(self, st):
+        """frames u8 [qn,h,w,3], cams f64 [qn,20] -> every stage of predict_batch, enqueued back to back."""
+        res, iters, R = self.cfg['ref_resolution'], self.cfg['refine_iter'], st['tables']['ref_num']
+        select, refine = self.selector._select_warped(res), self.refiner._refine_warped(128)
+
+        def fn(frames, cams):
+            det = self.detector._detect_u8(frames)                                  # [qn,4]: x, y, scale, score
+            crop, idx, sel_out, logits = select(ops.glue_detection_jobs(det, frames, res))
+            poses = ops.glue_initial_poses(det, idx, sel_out, st['refs'], cams)
+            chain = [poses]
+            for it in range(iters):
+                jobs, que_K, que_pose, rect, ref_Ks, ref_poses, _ = ops.glue_refine_problems(st['views'], R, cams, frames, poses, it > 0)
+                out = refine(jobs, que_K, que_pose, ref_Ks, ref_poses)
+                poses = ops.glue_apply_refinements(st['views'], que_pose, que_K, rect, out)
+                chain.append(poses)
+            return torch.stack(chain, 0), det, crop, idx, sel_out, logits
+        return fn
+
+    def _predict_batch_device(self, frames, que_Ks):
+        """predict_batch with cfg['device_glue']: one graph launch, one synchronising read at the end."""
+        st = self._glue_state()
+        qn = frames.shape[0]
+        with torch.no_grad():
+            cams = self.detector._to_dev(glue.cameras(np.stack(que_Ks, 0)))
+            outs = self.stages.run('predict', self._predict_device_fn(st), [frames, cams])
+            chain, det, crop, idx, sel_out, logits = [self.detector._to_host(t) for t in outs]
+        chain = chain.reshape(len(chain), qn, 3, 4)
+        poses0, refined = chain[0], [c.astype(np.float32) for c in chain[1:]]
+        inter = {'det_position': det[:, :2].copy(), 'det_scale_r2q': det[:, 2].copy(), 'det_que_img': crop,
+                 'sel_angle_r2q': sel_out[:, 0].copy(), 'sel_scores': logits, 'sel_ref_idx': idx,
+                 'refine_poses': [poses0] + refined}
+        return (refined[-1] if refined else poses0), inter
+
     # ------------------------------------------------------------------ throughput API
     def worker_clone(self):
         import copy
         other = copy.copy(self)
         other._workers, other._pool, other._workers_gen = None, None, None
+        other.stages = StageCache()                   # private graphs; the glue tables (self._glue) are shared, read-only
         other.detector, other.selector = self.detector.worker_clone(), self.selector.worker_clone()
         other.refiner = self.refiner.worker_clone() if self.refiner is not None else None
         return other

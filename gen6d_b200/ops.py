@@ -99,6 +99,49 @@ def warp_affine_u8(jobs, n_jobs, h, w):
     return _warp('g6d_warp_affine_u8', jobs, n_jobs, h, w)
 
 
+# ------------------------------------------------------------------------------- camera algebra between the stages
+def glue_detection_jobs(det_out, frames, size):
+    """det_out [qn,4] (g6d_det_parse) + frames u8 [qn,h,w,3] -> packed g6d_warp_job records [qn*88] of the selector crops."""
+    qn, h, w, _ = frames.shape
+    jobs = torch.empty(qn * WARP_JOB_BYTES, device=frames.device, dtype=torch.uint8)
+    _call('g6d_glue_detection_jobs', _p(det_out), _p(frames, torch.uint8), h, w, qn, size, _p(jobs, torch.uint8), _stream())
+    return jobs
+
+
+def glue_initial_poses(det_out, sel_idx, sel_out, refs_struct, cams):
+    """Detection + selection -> initial poses float64 [qn,12] (geometry.poses_from_similarity on the device)."""
+    qn = det_out.shape[0]
+    poses = torch.empty(qn, 12, device=det_out.device, dtype=torch.float64)
+    _call('g6d_glue_initial_poses', _p(det_out), _p(sel_idx, torch.int64), _p(sel_out), C.byref(refs_struct), _p(cams, torch.float64),
+          qn, _p(poses, torch.float64), _stream())
+    return poses
+
+
+def glue_refine_problems(views_struct, ref_num, cams, frames, poses, poses_are_f32):
+    """poses float64 [qn,12] -> (jobs u8 [qn*(ref_num+1)*88], que_K [qn,3,3], que_pose [qn,3,4], rect [qn,3,4],
+    ref_Ks [qn,R,3,3], ref_poses [qn,R,3,4], ref_rows i32 [qn,R]): geometry.refine_problems on the device."""
+    qn, h, w, _ = frames.shape
+    dev, f32 = frames.device, torch.float32
+    jobs = torch.empty(qn * (ref_num + 1) * WARP_JOB_BYTES, device=dev, dtype=torch.uint8)
+    que_K, que_pose, rect = torch.empty(qn, 3, 3, device=dev, dtype=f32), torch.empty(qn, 3, 4, device=dev, dtype=f32), \
+        torch.empty(qn, 3, 4, device=dev, dtype=f32)
+    ref_Ks, ref_poses = torch.empty(qn, ref_num, 3, 3, device=dev, dtype=f32), torch.empty(qn, ref_num, 3, 4, device=dev, dtype=f32)
+    rows = torch.empty(qn, ref_num, device=dev, dtype=torch.int32)
+    _call('g6d_glue_refine_problems', C.byref(views_struct), _p(cams, torch.float64), _p(frames, torch.uint8), h, w,
+          _p(poses, torch.float64), int(poses_are_f32), qn, _p(jobs, torch.uint8), _p(que_K), _p(que_pose), _p(rect), _p(ref_Ks),
+          _p(ref_poses), _p(rows, torch.int32), _stream())
+    return jobs, que_K, que_pose, rect, ref_Ks, ref_poses, rows
+
+
+def glue_apply_refinements(views_struct, que_pose, que_K, rect, net_out):
+    """Network output [qn,7] -> refined poses (float32 values) float64 [qn,12]: geometry.apply_refinements on the device."""
+    qn = net_out.shape[0]
+    poses = torch.empty(qn, 12, device=net_out.device, dtype=torch.float64)
+    _call('g6d_glue_apply_refinements', C.byref(views_struct), _p(que_pose), _p(que_K), _p(rect), _p(net_out), qn,
+          _p(poses, torch.float64), _stream())
+    return poses
+
+
 def imagenet_norm(x, out_c=4):
     out = torch.empty(*x.shape[:-1], out_c, device=x.device, dtype=torch.float32)
     _call('g6d_imagenet_norm', _p(x), _p(out), x.numel() // x.shape[-1], x.shape[-1], out_c, _stream())

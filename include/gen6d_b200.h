@@ -64,6 +64,64 @@ int g6d_warp_perspective_u8(const g6d_warp_job* jobs, int n_jobs, uint8_t* out, 
 /* cv2.warpAffine(src, M, (w, h), flags=INTER_LINEAR), same conventions: the detection crop of
  * estimator.py:184 (utils/base_utils.py:646-655 transformation_crop). */
 int g6d_warp_affine_u8(const g6d_warp_job* jobs, int n_jobs, uint8_t* out, int h, int w, g6d_stream_t stream);
+
+/* ---- camera algebra between the stages, on the device (estimator.py:176-214; utils/pose_utils.py:12-58,104-111,
+ * 217-244; utils/database_utils.py:8-25,54-139; dataset/database.py:400-404,667-694).  With these four launches a
+ * batched prediction detect -> select -> refine x N is one stream-ordered sequence with no host round trip.  The
+ * *_host variants run the identical code on host memory (unit tests against the numpy restatement). */
+typedef struct g6d_glue_camera {   /* one query frame; filled by the caller (numpy), float64 VALUES of:           */
+    double K[9];                   /*   the intrinsics,                                                           */
+    double Kinv[9];                /*   np.linalg.inv(K) evaluated in K's own dtype,                              */
+    double f;                      /*   (K[0,0] + K[1,1]) / 2 evaluated in K's own dtype,                         */
+    double f_sq;                   /*   f ** 2 evaluated in K's own dtype (a float32 K squares in float32)        */
+} g6d_glue_camera;
+typedef struct g6d_glue_refs {     /* the selector's reference views (device arrays, built once per object)       */
+    const double* poses;           /* [rfn,12] normalised reference poses (estimator.py:167 ref_info['poses'])    */
+    const double* cen;             /* [rfn,2]  projected object centre                                            */
+    const double* f;               /* [rfn]    (K00 + K11) / 2                                                    */
+    const double* dist;            /* [rfn]    |camera centre - object centre|                                    */
+    double center[3];
+} g6d_glue_refs;
+typedef struct g6d_glue_views {    /* the refiner's database views in unit-sphere coordinates (device arrays)     */
+    const double* poses;           /* [n,12] */
+    const double* R_look;          /* [n,9]  look-at rotation of every view                                        */
+    const double* RlookR;          /* [n,9]  R_look @ R                                                            */
+    const double* f;               /* [n]    focal length of the normalised crop                                   */
+    const double* Kinv;            /* [n,9]  */
+    const unsigned long long* src; /* [n]    device address of the view's uint8 [rows, cols, 3] image              */
+    const int* rows; const int* cols;
+    const int* even_idx;           /* [n_even] table rows of the FPS re-spread subset (database_utils.py:129-134)  */
+    const float* even_dirs;        /* [n_even,3] their unit viewing directions                                     */
+    int n_views, n_even, ref_num, size;
+    double norm_scale;             /* 2 / object diameter                                                          */
+    float norm_offset[3];          /* -norm_scale * object centre (float32, as numpy holds it)                     */
+    float size_scale;              /* float32(size * (1 - margin) / 2)                                             */
+} g6d_glue_views;
+/* det_out [qn,4] (x, y, scale, score; g6d_det_parse) -> the selector's crop jobs [qn] (g6d_warp_affine_u8), frame i at
+ * frames + i*rows*cols*3 */
+int g6d_glue_detection_jobs(const float* det_out, const uint8_t* frames, int rows, int cols, int qn, int size,
+                            g6d_warp_job* jobs, g6d_stream_t stream);
+int g6d_glue_detection_jobs_host(const float* det_out, const uint8_t* frames, int rows, int cols, int qn, int size,
+                                 g6d_warp_job* jobs);
+/* detection + selection (sel_idx [qn] int64, sel_out [qn,2] = angle, logit; g6d_sel_parse) -> poses float64 [qn,12] */
+int g6d_glue_initial_poses(const float* det_out, const long long* sel_idx, const float* sel_out, const g6d_glue_refs* refs,
+                           const g6d_glue_camera* cams, int qn, double* poses, g6d_stream_t stream);
+int g6d_glue_initial_poses_host(const float* det_out, const long long* sel_idx, const float* sel_out, const g6d_glue_refs* refs,
+                                const g6d_glue_camera* cams, int qn, double* poses);
+/* poses [qn,12] (float64 storage; poses_are_f32: the values are float32 poses, as after a refinement) -> everything one
+ * refinement stage reads: jobs [qn*(ref_num+1)] (query crop, then its views; g6d_warp_perspective_u8), que_K [qn,9],
+ * que_pose [qn,12], rect [qn,12], ref_Ks [qn,ref_num,9], ref_poses [qn,ref_num,12] (float32), ref_rows [qn,ref_num] */
+int g6d_glue_refine_problems(const g6d_glue_views* views, const g6d_glue_camera* cams, const uint8_t* frames, int rows, int cols,
+                             const double* poses, int poses_are_f32, int qn, g6d_warp_job* jobs, float* que_K, float* que_pose,
+                             float* rect, float* ref_Ks, float* ref_poses, int* ref_rows, g6d_stream_t stream);
+int g6d_glue_refine_problems_host(const g6d_glue_views* views, const g6d_glue_camera* cams, const uint8_t* frames, int rows,
+                                  int cols, const double* poses, int poses_are_f32, int qn, g6d_warp_job* jobs, float* que_K,
+                                  float* que_pose, float* rect, float* ref_Ks, float* ref_poses, int* ref_rows);
+/* network output [qn,7] (quaternion, offset, log2 scale) -> refined poses (float32 values in float64 storage) */
+int g6d_glue_apply_refinements(const g6d_glue_views* views, const float* que_pose, const float* que_K, const float* rect,
+                               const float* net_out, int qn, double* poses, g6d_stream_t stream);
+int g6d_glue_apply_refinements_host(const g6d_glue_views* views, const float* que_pose, const float* que_K, const float* rect,
+                                    const float* net_out, int qn, double* poses);
 /* (x - mean) / std on f32 [n_pixels, in_c] -> [n_pixels, out_c] (in_c, out_c in {3,4})
  * (network/detector.py:189, selector.py:115, refiner.py:65) */
 int g6d_imagenet_norm(const float* in, float* out, long long n_pixels, int in_c, int out_c, g6d_stream_t stream);

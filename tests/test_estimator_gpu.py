@@ -177,3 +177,96 @@ def test_add_and_prj_match_reference_over_20_frames(est):
     thr = float(np.median(A['obj_err']))
     clear = np.abs(A['obj_err'] - thr) > 0.05 * thr                    # frames not within 5 % of the threshold
     assert ((err[:, 1] < thr) == (A['obj_err'] < thr))[clear].all()
+
+
+def test_device_glue_kernels_equal_host_geometry(est):
+    """The four g6d_glue_* kernels (camera algebra between the stages, on the device) against geometry.py on the
+    same inputs: crop jobs bit for bit, poses / problem tensors to float32 rounding, same reference views."""
+    import torch
+    from gen6d_b200 import geometry as G, glue, ops
+    e, db = est
+    ids = e.refiner.ref_ids
+    e.cfg['device_glue'] = True
+    try:
+        st = e._glue_state()
+    finally:
+        e.cfg['device_glue'] = False
+    rng = np.random.RandomState(11)
+    qn = 6
+    imgs = [db.get_image(ids[3 + i]) for i in range(qn)]
+    frames = e.detector.upload_frame(imgs)
+    Ks = np.stack([db.get_K(ids[3 + i]) for i in range(qn)], 0)
+    cams = torch.from_numpy(glue.cameras(Ks)).cuda()
+    det = np.stack([rng.rand(qn) * 640, rng.rand(qn) * 480, 0.6 + rng.rand(qn), rng.rand(qn)], 1).astype(np.float32)
+    jobs = ops.glue_detection_jobs(torch.from_numpy(det).cuda(), frames, 128).cpu().numpy().view(G.WARP_JOB)
+    for i in range(qn):
+        np.testing.assert_array_equal(jobs['M'][i], G.affine_dst_to_src(G.crop_similarity(None, det[i, :2], 1 / det[i, 2], 0, 128)[1]))
+        assert jobs['src'][i] == frames[i].data_ptr() and (jobs['rows'][i], jobs['cols'][i]) == imgs[0].shape[:2]
+    idx = rng.randint(0, len(e.ref_info['poses']), qn)
+    sel = np.stack([rng.randn(qn) * 0.7, rng.randn(qn)], 1).astype(np.float32)
+    p0 = ops.glue_initial_poses(torch.from_numpy(det).cuda(), torch.from_numpy(idx).cuda(), torch.from_numpy(sel).cuda(), st['refs'], cams)
+    want0 = G.poses_from_similarity(det[:, :2], det[:, 2], sel[:, 0], e.ref_info['poses'][idx], e.ref_info['Ks'][idx], Ks, e.ref_info['center'])
+    got0 = p0.cpu().numpy().reshape(qn, 3, 4)
+    np.testing.assert_allclose(got0[:, :, :3], want0[:, :, :3], atol=2e-7)
+    np.testing.assert_allclose(got0[:, :, 3], want0[:, :, 3], rtol=5e-7, atol=5e-7)
+    # refinement problems at real poses (float64 first, float32 afterwards)
+    poses = np.stack([db.get_pose(ids[5 + i]) for i in range(qn)], 0).astype(np.float64)
+    poses[:, :, 3] += rng.randn(qn, 3) * 0.01
+    for f32 in (False, True):
+        ps = poses.astype(np.float32) if f32 else poses
+        want = G.refine_problems(e.refiner.ref_database, ids, Ks, ps, 128, 6, True)
+        out = ops.glue_refine_problems(st['views'], 6, cams, frames, torch.from_numpy(ps.astype(np.float64).reshape(qn, 12)).cuda(), f32)
+        jobs_r, que_K, que_pose, rect, ref_Ks, ref_poses, rows = [t.cpu().numpy() for t in out]
+        assert [[st['tables']['ids'][r] for r in row] for row in rows] == [[str(v) for v in row] for row in want['ref_ids']]
+        rel = lambda a, b: float(np.abs(a - b).max() / np.abs(b).max())
+        for name, a, b in (('que_K', que_K, want['que_K']), ('que_pose', que_pose, want['que_pose']), ('rect', rect, want['pose_rect']),
+                           ('ref_Ks', ref_Ks, want['ref_Ks']), ('ref_poses', ref_poses, want['ref_poses'])):
+            assert rel(a, b) < 5e-7, (name, rel(a, b))
+        jr = jobs_r.view(G.WARP_JOB).reshape(qn, 7)
+        srcs = e.refiner._ref_sources(ids)
+        for i in range(qn):
+            Hs = [want['que_H'][i]] + list(want['ref_Hs'][i])
+            for j, H in enumerate(Hs):
+                np.testing.assert_allclose(jr['M'][i, j], G.perspective_dst_to_src(H), rtol=3e-6, atol=1e-9)
+            assert jr['src'][i, 0] == frames[i].data_ptr()
+            assert [int(v) for v in jr['src'][i, 1:]] == [srcs[r][0] for r in rows[i]]
+        # the update from identical problem tensors
+        net = (rng.randn(qn, 7) * 0.05).astype(np.float32)
+        net[:, 0] += 1
+        net[:, :4] /= np.linalg.norm(net[:, :4], axis=1, keepdims=True)
+        dev = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
+        got = ops.glue_apply_refinements(st['views'], dev(want['que_pose']), dev(want['que_K']), dev(want['pose_rect']), dev(net))
+        new = G.apply_refinements(want, net[:, :4], net[:, 4:6], [2.0 ** o[6] for o in net])
+        np.testing.assert_allclose(got.cpu().numpy().reshape(qn, 3, 4), new, atol=5e-7)
+
+
+def test_device_glue_prediction_equals_host_path(est):
+    """cfg['device_glue']: the whole batch prediction as one captured graph (no host between the stages) gives the
+    host-sequenced predict_batch's detections / selections exactly, its initial poses to float32 rounding, and refined
+    poses inside the model's own sensitivity bound (the two paths differ by float32 rounding of the crop cameras)."""
+    e, db = est
+    ids = db.get_img_ids()[:4]
+    imgs, Ks = [db.get_image(i) for i in ids], [db.get_K(i) for i in ids]
+    host_poses, host = e.predict_batch(imgs, Ks)
+    e.cfg['device_glue'] = True
+    try:
+        dev_poses, dev = e.predict_batch(imgs, Ks)
+        again, _ = e.predict_batch(imgs, Ks)
+        many = e.predict_many(imgs, Ks, workers=2, batch=2)
+    finally:
+        e.cfg['device_glue'] = False
+    np.testing.assert_array_equal(dev['det_position'], host['det_position'])
+    np.testing.assert_array_equal(dev['det_scale_r2q'], host['det_scale_r2q'])
+    np.testing.assert_array_equal(dev['sel_ref_idx'], host['sel_ref_idx'])
+    np.testing.assert_array_equal(dev['sel_angle_r2q'], host['sel_angle_r2q'])
+    np.testing.assert_array_equal(dev['det_que_img'], host['det_que_img'])
+    np.testing.assert_array_equal(dev_poses, again)                                # replay-deterministic
+    ch_d, ch_h = np.stack([np.asarray(p, np.float64) for p in dev['refine_poses']]), np.stack([np.asarray(p, np.float64) for p in host['refine_poses']])
+    d = np.abs(ch_d - ch_h).reshape(len(ch_d), -1).max(1)
+    print('device glue vs host path, max |dpose| per iteration', d)
+    assert d[0] < 5e-6
+    S = np.load(os.path.join(HERE, 'golden', 'sens_golden.npz'))
+    assert d[1] < 2e-4 and (d[1:] <= np.maximum(2.0 * S['gain_R'][1:] * 1e-3, 2e-3)).all()
+    assert dev_poses.dtype == np.float32 and dev_poses.shape == (4, 3, 4)
+    for j, (p, one) in enumerate(many):
+        assert np.abs(p - ch_h[-1, j]).max() <= max(2.0 * S['gain_R'][-1] * 1e-3, 2e-3) and int(one['sel_ref_idx']) == int(host['sel_ref_idx'][j])
