@@ -35,7 +35,6 @@ sys.path.insert(0, ROOT)
 E2E_WORKERS = int(os.environ.get('G6D_E2E_WORKERS', '2'))      # host threads / CUDA streams per GPU (predict_many / device lanes)
 E2E_BATCH = int(os.environ.get('G6D_E2E_BATCH', '0'))          # frames per batched stage (predict_batch); 0 = pick_batch(steps)
 E2E_MAX_BATCH = 10
-DEVICE_GLUE = os.environ.get('G6D_DEVICE_GLUE', '0') != '0'     # camera algebra between the stages on the device: one graph per batch
 
 
 def pick_batch(steps, workers):
@@ -352,7 +351,7 @@ def run_ours(args, rank, world, local_rank):
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
-    est, db = syn.build_estimator(device_glue=DEVICE_GLUE)
+    est, db = syn.build_estimator()
     note('estimator built')
     ids = db.get_img_ids()
     frames = [ids[(7 + rank * 13 + i * 3) % len(ids)] for i in range(8)]   # different frames per rank
@@ -553,7 +552,7 @@ def run_ours(args, rank, world, local_rank):
             'warmup': args.warmup, 'ms_per_step': dev_ms / args.steps, 'higher_is_better': True, 'scaling': 'weak',
             'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
             'config': {'workload': WORKLOAD, 'parallelism': f'replica x{world} (independent frames per GPU); per GPU {E2E_WORKERS} lanes (streams) x batches of '
-                                                            f'{Bt} frames through the batched stages = {E2E_WORKERS * Bt} frames in flight',
+                                                            f'{Bt} frames through the batched stages = {E2E_WORKERS * Bt} frames in flight' + ('; camera algebra between the stages on the device, one captured graph per batch' if est.cfg['device_glue'] else '; stages sequenced by the host'),
                        'l2': 'per-step working set (220 MB selector reference stack + 300 MB weights + detector '
                              'activations) exceeds the 126 MB L2; no explicit flush'},
             'e2e': {'value': world * args.steps / (pipe_ms * 1e-3), 'unit': 'poses/s', 'ms_per_step': pipe_ms / args.steps,

@@ -6,6 +6,8 @@ k+1 on pose k), so this class keeps the reference's structure; throughput comes 
 from keeping every reference-side tensor resident on the device, and from running independent
 frames on independent GPUs (see gen6d_b200/dist.py).
 """
+import os
+
 import numpy as np
 import torch
 import yaml
@@ -29,8 +31,10 @@ class Gen6DEstimator:
         'device_build': False,    # True: cut the 64 + 5x64 reference crops of build() with the device warp kernel (row f2)
         'host_warps': False,      # True: keep the between-stage crops on the host in OpenCV, as the reference does
         'host_threads': None,     # OpenCV / torch-CPU threads for the host geometry (None: min(8, usable CPUs))
-        'device_glue': False,     # True: predict_batch keeps the camera algebra between the stages on the device -- the
-                                  # whole batch prediction is ONE captured graph (csrc/glue.cu), no host round trips
+        # predict_batch / predict_many(batch > 1) keep the camera algebra between the stages on the device: the whole
+        # batch prediction is ONE captured graph (csrc/glue.cu), no host round trips.  False (or G6D_DEVICE_GLUE=0):
+        # the host sequences the stages with numpy geometry in between, as predict() does.
+        'device_glue': os.environ.get('G6D_DEVICE_GLUE', '1') != '0',
     }
 
     def __init__(self, cfg, modules=None):
@@ -261,7 +265,8 @@ class Gen6DEstimator:
             self._warm = set()
         n = len(que_imgs)
         batch = max(1, min(batch, n))
-        if batch not in self._warm:                  # capture every worker's stage graphs for this batch size, one at a time
+        warm_key = (batch, bool(self.cfg['device_glue']))
+        if warm_key not in self._warm:               # capture every worker's graphs for this batch size / path, one at a time
             for est, stream in self._workers:
                 stream.wait_stream(torch.cuda.current_stream())
                 with torch.cuda.stream(stream):
@@ -270,7 +275,7 @@ class Gen6DEstimator:
                     else:
                         est.predict_batch([que_imgs[i % n] for i in range(batch)], [que_Ks[i % n] for i in range(batch)])
                     stream.synchronize()
-            self._warm.add(batch)
+            self._warm.add(warm_key)
         results = [None] * n
         caller = torch.cuda.current_stream()
         chunks = [list(range(b, min(b + batch, n))) for b in range(0, n, batch)]

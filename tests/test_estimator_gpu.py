@@ -186,11 +186,7 @@ def test_device_glue_kernels_equal_host_geometry(est):
     from gen6d_b200 import geometry as G, glue, ops
     e, db = est
     ids = e.refiner.ref_ids
-    e.cfg['device_glue'] = True
-    try:
-        st = e._glue_state()
-    finally:
-        e.cfg['device_glue'] = False
+    st = e._glue_state()
     rng = np.random.RandomState(11)
     qn = 6
     imgs = [db.get_image(ids[3 + i]) for i in range(qn)]
@@ -247,14 +243,16 @@ def test_device_glue_prediction_equals_host_path(est):
     e, db = est
     ids = db.get_img_ids()[:4]
     imgs, Ks = [db.get_image(i) for i in ids], [db.get_K(i) for i in ids]
-    host_poses, host = e.predict_batch(imgs, Ks)
-    e.cfg['device_glue'] = True
+    was = e.cfg['device_glue']
     try:
+        e.cfg['device_glue'] = False
+        host_poses, host = e.predict_batch(imgs, Ks)
+        e.cfg['device_glue'] = True
         dev_poses, dev = e.predict_batch(imgs, Ks)
         again, _ = e.predict_batch(imgs, Ks)
         many = e.predict_many(imgs, Ks, workers=2, batch=2)
     finally:
-        e.cfg['device_glue'] = False
+        e.cfg['device_glue'] = was
     np.testing.assert_array_equal(dev['det_position'], host['det_position'])
     np.testing.assert_array_equal(dev['det_scale_r2q'], host['det_scale_r2q'])
     np.testing.assert_array_equal(dev['sel_ref_idx'], host['sel_ref_idx'])
