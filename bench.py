@@ -270,14 +270,14 @@ def sharded_section(world, rank, note=lambda what: None):
     local = build('selector', {'selector_angle_num': bins})
     local.load_ref_imgs(np.ascontiguousarray(imgs[:, r0:r1]), poses[r0:r1], center, vert)
     note('sharded: unsharded selector loaded')
-    t_local = timed(lambda: local.select_que_imgs(que), 5)
+    t_local = timed(lambda: local.select_que_imgs(que), 12, warm=3)
     note('sharded: unsharded selector timed')
     del local
     torch.cuda.empty_cache()
     sel = gdist.shard_selector(build('selector', {'selector_angle_num': bins}), comm)
     sel.load_ref_imgs(imgs, poses, center, vert)
     note('sharded: sharded selector loaded')
-    t_shard = timed(lambda: sel.select_que_imgs(que), 5)
+    t_shard = timed(lambda: sel.select_que_imgs(que), 12, warm=3)      # 12 queries: one host hiccup no longer moves the mean by 25 %
     note('sharded: sharded selector timed')
     out['selector_ref_shard'] = {
         'workload': f'{refs} refs x {bins} bins over {world} GPUs ({per_gpu_refs} refs = {per_gpu_refs * bins} slices = '
