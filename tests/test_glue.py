@@ -94,3 +94,18 @@ def test_refine_problems_and_updates_equal_numpy(db):
         assert mine.dtype == np.float64
         np.testing.assert_allclose(mine, new, rtol=0, atol=3e-7)
         np.testing.assert_array_equal(mine, mine.astype(np.float32).astype(np.float64))      # float32 values
+
+
+def test_small_reference_set_and_float64_intrinsics():
+    """Fewer database views than the 128-view FPS subset, intrinsics given as float64."""
+    small = SyntheticObjectDatabase(**{**cases.estimator_case()['db'], 'n_views': 40})
+    ids = small.get_img_ids()
+    tables = glue.refiner_views(small, ids, 128, 6)
+    assert len(ids) == 40 and 6 <= len(tables['even_idx']) <= 40        # the FPS re-spread of the whole (small) set
+    poses = np.stack(perturbed_poses(small, 8, 9), 0)
+    Ks = np.stack([small.K.astype(np.float64)] * len(poses), 0)
+    want = G.refine_problems(small, ids, Ks, poses, 128, 6, True)
+    got = glue.host_refine_problems(tables, glue.cameras(Ks), poses, False, 480, 640)
+    assert [[tables['ids'][r] for r in row] for row in got['ref_rows']] == [[str(v) for v in row] for row in want['ref_ids']]
+    for k in ('que_K', 'que_pose', 'pose_rect', 'ref_Ks', 'ref_poses'):
+        assert float(np.abs(got[k] - want[k]).max() / np.abs(want[k]).max()) < 3e-7, k
